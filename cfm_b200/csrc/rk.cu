@@ -1,0 +1,311 @@
+// Dormand-Prince 5(4) lock-step driver pieces (torchdyn NeuralODE(solver="dopri5") semantics;
+// call sites in the reference: examples/2D_tutorials/tutorial_training_8_gaussians_to_moons.ipynb
+// :332-338; torchdyn itself is un-vendored -- SURVEY.md Appendix B).
+//
+// The whole batch advances with ONE scalar step size (global RMS error norm), so the step
+// controller is a handful of scalars.  They live in a device struct (cfm_rk_state): every kernel
+// of a step reads t/dt from it, the error norm is accumulated into it, and a one-thread control
+// kernel does accept/reject, checkpoint clipping and step-size adaptation in fp32 exactly in the
+// order torchdyn's _adaptive_odeint does.  A full step (6 stage-input kernels + 6 MLP forwards +
+// error norm + control + commit) is therefore enqueued without any host round trip.
+//
+// Buffers (fp32, numel = B*D each): x, xnew, xs (stage input), k[0..6] contiguous (k1..k7).
+// All elementwise kernels are HBM-bound: float4 accesses, grid = 4 CTAs/SM, grid-stride loops.
+#include "common.cuh"
+
+namespace cfm {
+
+__constant__ float kC[7] = {0.f, 1.f / 5, 3.f / 10, 4.f / 5, 8.f / 9, 1.f, 1.f};
+__constant__ float kA[7][6] = {
+    {0, 0, 0, 0, 0, 0},
+    {1.f / 5, 0, 0, 0, 0, 0},
+    {3.f / 40, 9.f / 40, 0, 0, 0, 0},
+    {44.f / 45, -56.f / 15, 32.f / 9, 0, 0, 0},
+    {19372.f / 6561, -25360.f / 2187, 64448.f / 6561, -212.f / 729, 0, 0},
+    {9017.f / 3168, -355.f / 33, 46732.f / 5247, 49.f / 176, -5103.f / 18656, 0},
+    {35.f / 384, 0.f, 500.f / 1113, 125.f / 192, -2187.f / 6784, 11.f / 84}};
+// b5 - b4 (embedded error weights), k1..k7
+__constant__ float kE[7] = {(float)(35.0 / 384 - 1951.0 / 21600), 0.f,
+                            (float)(500.0 / 1113 - 22642.0 / 50085),
+                            (float)(125.0 / 192 - 451.0 / 720),
+                            (float)(-2187.0 / 6784 + 12231.0 / 42400),
+                            (float)(11.0 / 84 - 649.0 / 6300), (float)(-1.0 / 60)};
+
+static inline int ew_grid(int64_t numel) {
+  int64_t blocks = (numel / 4 + 255) / 256 + 1;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  return (int)(blocks < cap ? blocks : cap);
+}
+
+__device__ __forceinline__ double block_sum_to(double v, double* smem32) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) smem32[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (warp == 0) {
+    t = lane < (blockDim.x >> 5) ? smem32[lane] : 0.0;
+    t = warp_sum(t);
+  }
+  return t;  // valid in warp 0 lane 0
+}
+
+// xs (stage 1..5) or xnew (stage 6) = x + dt * sum_j a[stage][j] * k_j ; also t_stage = t + c*dt
+__global__ void rk_stage_input_kernel(const cfm_rk_state* __restrict__ st, const float* __restrict__ x,
+                                      const float* __restrict__ k, float* __restrict__ out,
+                                      float* __restrict__ t_stage, int64_t numel, int stage) {
+  if (st->done) return;
+  const float dt = st->dt;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && t_stage) *t_stage = st->t + kC[stage] * dt;
+  float a[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) a[j] = dt * kA[stage][j];
+  const int64_t n4 = (numel & 3) ? 0 : (numel >> 2);  // k_j bases stay 16B-aligned only then
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = reinterpret_cast<const float4*>(x)[i];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      if (j < stage && kA[stage][j] != 0.f) {
+        const float4 kk = reinterpret_cast<const float4*>(k + (int64_t)j * numel)[i];
+        v.x = fmaf(a[j], kk.x, v.x); v.y = fmaf(a[j], kk.y, v.y);
+        v.z = fmaf(a[j], kk.z, v.z); v.w = fmaf(a[j], kk.w, v.w);
+      }
+    }
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
+    float v = x[i];
+    for (int j = 0; j < stage; ++j) v = fmaf(a[j], k[(int64_t)j * numel + i], v);
+    out[i] = v;
+  }
+}
+
+// err_acc += sum( (dt * sum_j e_j k_j / (atol + rtol * max(|x|, |xnew|)))^2 )
+__global__ void rk_error_norm_kernel(cfm_rk_state* st, const float* __restrict__ x,
+                                     const float* __restrict__ xnew, const float* __restrict__ k,
+                                     int64_t numel) {
+  __shared__ double red[32];
+  if (st->done) return;
+  const float dt = st->dt, atol = st->atol, rtol = st->rtol;
+  double acc = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
+    float e = 0.f;
+#pragma unroll
+    for (int j = 0; j < 7; ++j)
+      if (kE[j] != 0.f) e = fmaf(kE[j], k[(int64_t)j * numel + i], e);
+    e *= dt;
+    const float tol = atol + rtol * fmaxf(fabsf(x[i]), fabsf(xnew[i]));
+    const float r = e / tol;
+    acc += (double)r * (double)r;
+  }
+  const double t = block_sum_to(acc, red);
+  if (threadIdx.x == 0) atomicAdd(&st->err_acc, t);
+}
+
+__device__ __forceinline__ void rk_prestep(cfm_rk_state* st, const float* t_span) {
+  // top of torchdyn's while-loop for the NEXT step: clip to T, clip to the next checkpoint
+  if (!(st->t < st->t_end)) { st->done = 1; return; }
+  if (st->t + st->dt > st->t_end) st->dt = st->t_end - st->t;
+  if (st->ckpt < st->n_span && st->t + st->dt > t_span[st->ckpt]) {
+    st->dt_old = st->dt;
+    st->ckpt_flag = 1;
+    st->dt = t_span[st->ckpt] - st->t;
+  }
+}
+
+__global__ void rk_control_kernel(cfm_rk_state* st, const float* __restrict__ t_span, int64_t numel) {
+  if (st->done) return;
+  const float ratio = (float)sqrt(st->err_acc / (double)numel);
+  st->ratio = ratio;
+  st->err_acc = 0.0;
+  st->nfe += 6;
+  const bool accept = ratio <= 1.f;
+  st->save_slot = -1;
+  st->commit = accept ? 1 : 0;
+  if (accept) {
+    float tn = st->t + st->dt;
+    // torchdyn records a checkpoint when t + dt == t_span[ckpt]; a step that was clipped to land
+    // on the checkpoint is snapped onto it so fp32 rounding of t + (t_ckpt - t) cannot miss it
+    if (st->ckpt < st->n_span && (tn == t_span[st->ckpt] || st->ckpt_flag)) {
+      tn = t_span[st->ckpt];
+      st->save_slot = st->ckpt;
+      st->ckpt++;
+    }
+    st->t = tn;
+    st->accepted++;
+  } else {
+    st->rejected++;
+  }
+  float dt = st->dt;
+  if (st->ckpt_flag) { dt = st->dt_old - dt; st->ckpt_flag = 0; }
+  // adapt_step(dt, ratio, safety=.9, min_factor=.2, max_factor=10, order=5)
+  if (ratio == 0.f) {
+    dt = dt * 10.f;
+  } else {
+    const float min_factor = ratio < 1.f ? 1.f : 0.2f;
+    const float factor = fminf(10.f, fmaxf(0.9f / powf(ratio, 0.2f), min_factor));
+    dt = dt * factor;
+  }
+  st->dt = dt;
+  rk_prestep(st, t_span);
+}
+
+// accepted: x <- xnew, k1 <- k7 (FSAL), optional checkpoint copy
+__global__ void rk_commit_kernel(const cfm_rk_state* __restrict__ st, float* __restrict__ x,
+                                 const float* __restrict__ xnew, float* __restrict__ k,
+                                 float* __restrict__ traj, int64_t numel) {
+  if (!st->commit) return;
+  const int slot = st->save_slot;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const float* k7 = k + 6 * numel;
+  const int64_t n4 = (numel & 3) ? 0 : (numel >> 2);  // k_j bases stay 16B-aligned only then
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(xnew)[i];
+    reinterpret_cast<float4*>(x)[i] = v;
+    reinterpret_cast<float4*>(k)[i] = reinterpret_cast<const float4*>(k7)[i];
+    if (slot >= 0) reinterpret_cast<float4*>(traj + (int64_t)slot * numel)[i] = v;
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
+    x[i] = xnew[i];
+    k[i] = k7[i];
+    if (slot >= 0) traj[(int64_t)slot * numel + i] = xnew[i];
+  }
+}
+
+// ---- Hairer initial step (torchdyn init_step) -------------------------------------------------
+// scratch[0] = sum (x/scale)^2, scratch[1] = sum (f0/scale)^2, scratch[2] = sum ((f1-f0)/scale)^2
+__global__ void rk_init_reduce_a(const cfm_rk_state* __restrict__ st, const float* __restrict__ x,
+                                 const float* __restrict__ f0, double* scratch, int64_t numel) {
+  __shared__ double red[32];
+  const float atol = st->atol, rtol = st->rtol;
+  double a0 = 0.0, a1 = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
+    const float sc = atol + fabsf(x[i]) * rtol;
+    const float p = x[i] / sc, q = f0[i] / sc;
+    a0 += (double)p * p;
+    a1 += (double)q * q;
+  }
+  double t = block_sum_to(a0, red);
+  if (threadIdx.x == 0) atomicAdd(&scratch[0], t);
+  __syncthreads();
+  t = block_sum_to(a1, red);
+  if (threadIdx.x == 0) atomicAdd(&scratch[1], t);
+}
+__device__ __forceinline__ float rk_h0(const double* scratch, int64_t numel) {
+  const float d0 = (float)sqrt(scratch[0] / (double)numel);
+  const float d1 = (float)sqrt(scratch[1] / (double)numel);
+  return (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : 0.01f * d0 / d1;
+}
+__global__ void rk_init_probe(cfm_rk_state* st, const float* __restrict__ x, const float* __restrict__ f0,
+                              float* __restrict__ x_probe, float* __restrict__ t_stage,
+                              const double* __restrict__ scratch, int64_t numel) {
+  const float h0 = rk_h0(scratch, numel);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    st->dt_old = h0;
+    if (t_stage) *t_stage = st->t + h0;
+  }
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride)
+    x_probe[i] = fmaf(h0, f0[i], x[i]);
+}
+__global__ void rk_init_reduce_b(const cfm_rk_state* __restrict__ st, const float* __restrict__ x,
+                                 const float* __restrict__ f0, const float* __restrict__ f1,
+                                 double* scratch, int64_t numel) {
+  __shared__ double red[32];
+  const float atol = st->atol, rtol = st->rtol;
+  double a = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
+    const float sc = atol + fabsf(x[i]) * rtol;
+    const float q = (f1[i] - f0[i]) / sc;
+    a += (double)q * q;
+  }
+  const double t = block_sum_to(a, red);
+  if (threadIdx.x == 0) atomicAdd(&scratch[2], t);
+}
+__global__ void rk_init_finish(cfm_rk_state* st, const float* __restrict__ t_span,
+                               const double* __restrict__ scratch, int64_t numel) {
+  const float h0 = rk_h0(scratch, numel);
+  const float d1 = (float)sqrt(scratch[1] / (double)numel);
+  const float d2 = (float)sqrt(scratch[2] / (double)numel) / h0;
+  float h1;
+  if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, h0 * 1e-3f);
+  else h1 = powf(0.01f / fmaxf(d1, d2), 1.f / 6.f);
+  st->dt = fminf(100.f * h0, h1);
+  st->nfe += 2;
+  st->ckpt = 1;
+  st->ckpt_flag = 0;
+  st->done = 0;
+  rk_prestep(st, t_span);
+}
+
+__global__ void axpy_kernel(const float* __restrict__ x, const float* __restrict__ k, float h,
+                            float* __restrict__ out, int64_t numel) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride)
+    out[i] = fmaf(h, k[i], x[i]);
+}
+
+}  // namespace cfm
+
+using namespace cfm;
+
+#define RK_CHECK(cond) CFM_REQUIRE(cond, "%s: bad argument (" #cond ")", __func__)
+
+extern "C" int cfm_rk_stage_input(const cfm_rk_state* st, const float* x, const float* k, float* out,
+                                  float* t_stage, int64_t numel, int stage, void* stream) {
+  RK_CHECK(st && x && k && out && numel > 0 && stage >= 1 && stage <= 6);
+  RK_CHECK(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(out)) & 15) == 0);
+  rk_stage_input_kernel<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(st, x, k, out, t_stage, numel, stage);
+  CFM_CUDA_OK(cudaGetLastError());
+  return CFM_OK;
+}
+extern "C" int cfm_rk_error_norm(cfm_rk_state* st, const float* x, const float* xnew, const float* k,
+                                 int64_t numel, void* stream) {
+  RK_CHECK(st && x && xnew && k && numel > 0);
+  rk_error_norm_kernel<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(st, x, xnew, k, numel);
+  CFM_CUDA_OK(cudaGetLastError());
+  return CFM_OK;
+}
+extern "C" int cfm_rk_control(cfm_rk_state* st, const float* t_span, int64_t numel, void* stream) {
+  RK_CHECK(st && t_span && numel > 0);
+  rk_control_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(st, t_span, numel);
+  CFM_CUDA_OK(cudaGetLastError());
+  return CFM_OK;
+}
+extern "C" int cfm_rk_commit(const cfm_rk_state* st, float* x, const float* xnew, float* k, float* traj,
+                             int64_t numel, void* stream) {
+  RK_CHECK(st && x && xnew && k && traj && numel > 0);
+  rk_commit_kernel<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(st, x, xnew, k, traj, numel);
+  CFM_CUDA_OK(cudaGetLastError());
+  return CFM_OK;
+}
+extern "C" int cfm_rk_init_a(cfm_rk_state* st, const float* x, const float* f0, float* x_probe,
+                             float* t_stage, double* scratch, int64_t numel, void* stream) {
+  RK_CHECK(st && x && f0 && x_probe && scratch && numel > 0);
+  cudaStream_t s = (cudaStream_t)stream;
+  CFM_CUDA_OK(cudaMemsetAsync(scratch, 0, 4 * sizeof(double), s));
+  rk_init_reduce_a<<<ew_grid(numel), 256, 0, s>>>(st, x, f0, scratch, numel);
+  rk_init_probe<<<ew_grid(numel), 256, 0, s>>>(st, x, f0, x_probe, t_stage, scratch, numel);
+  CFM_CUDA_OK(cudaGetLastError());
+  return CFM_OK;
+}
+extern "C" int cfm_rk_init_b(cfm_rk_state* st, const float* x, const float* f0, const float* f1,
+                             const float* t_span, double* scratch, int64_t numel, void* stream) {
+  RK_CHECK(st && x && f0 && f1 && t_span && scratch && numel > 0);
+  cudaStream_t s = (cudaStream_t)stream;
+  rk_init_reduce_b<<<ew_grid(numel), 256, 0, s>>>(st, x, f0, f1, scratch, numel);
+  rk_init_finish<<<1, 1, 0, s>>>(st, t_span, scratch, numel);
+  CFM_CUDA_OK(cudaGetLastError());
+  return CFM_OK;
+}
+extern "C" int cfm_axpy_f32(const float* x, const float* k, float h, float* x_out, int64_t numel,
+                            void* stream) {
+  RK_CHECK(x && k && x_out && numel > 0);
+  axpy_kernel<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(x, k, h, x_out, numel);
+  CFM_CUDA_OK(cudaGetLastError());
+  return CFM_OK;
+}

@@ -1,0 +1,245 @@
+// Pair sampling from a coupling:  (i, j) ~ pi   (reference: torchcfm/optimal_transport.py:116-121)
+//
+// The reference flattens the float64 plan, normalises it, and calls np.random.choice, i.e.
+//   cdf = cumsum(p) / cumsum(p)[-1];  k = searchsorted(cdf, uniform, side='right');  (i, j) = divmod(k, n1)
+// Here the N^2 plan is never materialised.  The inverse CDF is evaluated hierarchically:
+//   1. row masses r_i = sum_j pi_ij (one warp per row, float64 accumulation, one pass over M),
+//   2. an in-block float64 scan of r -> row cdf (n0 entries),
+//   3. per draw (one warp each): binary-search the row, then a warp-scan along that row of pi
+//      entries recomputed from (M, log_u, log_v) to find the column where the cdf crosses.
+// This equals the flat searchsorted up to float64 rounding of the cumulative sums.  The uniforms
+// come from the host's np.random stream so the reference's RNG contract is kept.
+#include "common.cuh"
+
+namespace cfm {
+
+struct PotEntry {  // pi_ij = exp(-M_ij/reg + lu_i + lv_j), NumPy's fp32 rounding of -M/reg
+  const float* M;
+  int64_t ldm;
+  float reg;
+  const float* cost_max;  // device scalar, read when normalize != 0
+  int normalize;
+  const double* lu;
+  const double* lv;
+  __device__ __forceinline__ double operator()(int i, int j) const {
+    float m = __ldg(M + (int64_t)i * ldm + j);
+    if (normalize) m = __fdiv_rn(m, __ldg(cost_max));
+    const double e = (double)(-__fdiv_rn(m, reg)) + lu[i] + lv[j];
+    return (double)expf((float)e);
+  }
+};
+struct DenseEntry {
+  const double* P;
+  int64_t ld;
+  __device__ __forceinline__ double operator()(int i, int j) const { return P[(int64_t)i * ld + j]; }
+};
+
+template <class E>
+__global__ void row_mass_kernel(E ent, int n0, int n1, double* __restrict__ rowmass, int32_t* status) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n0) return;
+  double s = 0.0;
+  for (int j = lane; j < n1; j += 32) s += ent(warp, j);
+  s = warp_sum(s);
+  if (lane == 0) {
+    rowmass[warp] = s;
+    if (!isfinite(s) && status) atomicOr(status, CFM_FLAG_NONFINITE);
+  }
+}
+
+// <P, M> = sum_ij pi_ij * M_ij  (pot.sinkhorn2, torchcfm/optimal_transport.py:288,300)
+__global__ void plan_dot_cost_kernel(PotEntry ent, int n0, int n1, double* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n0) return;
+  const float cm = ent.normalize ? __ldg(ent.cost_max) : 1.f;
+  double s = 0.0;
+  for (int j = lane; j < n1; j += 32) {
+    float m = __ldg(ent.M + (int64_t)warp * ent.ldm + j);
+    if (ent.normalize) m = __fdiv_rn(m, cm);
+    s += ent(warp, j) * (double)m;
+  }
+  s = warp_sum(s);
+  if (lane == 0 && s != 0.0) atomicAdd(out, s);
+}
+
+// single CTA: inclusive float64 scan of rowmass[0..n) -> rowcdf; rowcdf[n] = total
+__global__ void __launch_bounds__(1024) row_cdf_kernel(const double* __restrict__ rowmass, int n,
+                                                       double* __restrict__ rowcdf, int32_t* status) {
+  __shared__ double wsum[32];
+  __shared__ double carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (n + 1023) / 1024;
+  const int beg = min(n, tid * per), end = min(n, beg + per);
+  double local = 0.0;
+  for (int i = beg; i < end; ++i) local += rowmass[i];
+  // block exclusive scan of `local`
+  double incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    double w = wsum[lane];
+    double wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    wsum[lane] = wi - w;  // exclusive prefix of warp sums
+    if (lane == 31) carry_s = wi;
+  }
+  __syncthreads();
+  double run = wsum[warp] + (incl - local);
+  for (int i = beg; i < end; ++i) {
+    run += rowmass[i];
+    rowcdf[i] = run;
+  }
+  if (tid == 0) {
+    rowcdf[n] = carry_s;
+    if (status && fabs(carry_s) < 1e-8) atomicOr(status, CFM_FLAG_ZERO_MASS);
+  }
+}
+
+template <class E>
+__global__ void draw_kernel(E ent, int n0, int n1, const double* __restrict__ rowcdf,
+                            const double* __restrict__ uniforms, int n_draws,
+                            int64_t* __restrict__ i_out, int64_t* __restrict__ j_out) {
+  const int draw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (draw >= n_draws) return;
+  const double total = rowcdf[n0];
+  const double u = uniforms[draw];
+  if (!(fabs(total) >= 1e-8)) {
+    // optimal_transport.py:93-96: uniform plan
+    if (lane == 0) {
+      const int64_t size = (int64_t)n0 * n1;
+      int64_t k = (int64_t)(u * (double)size);
+      if (k >= size) k = size - 1;
+      i_out[draw] = k / n1;
+      j_out[draw] = k % n1;
+    }
+    return;
+  }
+  const double target = u * total;
+  // first row with rowcdf[i] > target
+  int lo = 0, hi = n0 - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (rowcdf[mid] > target) hi = mid; else lo = mid + 1;
+  }
+  const int i = lo;
+  double run = i > 0 ? rowcdf[i - 1] : 0.0;
+  int jsel = -1, jlast_pos = -1;
+  for (int j0 = 0; j0 < n1 && jsel < 0; j0 += 32) {
+    const int j = j0 + lane;
+    const double v = j < n1 ? ent(i, j) : 0.0;
+    double incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const bool hit = (j < n1) && (run + incl > target);
+    const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+    const unsigned pos = __ballot_sync(0xffffffffu, (j < n1) && v > 0.0);
+    if (pos) jlast_pos = j0 + 31 - __clz(pos);
+    if (ballot) jsel = j0 + __ffs(ballot) - 1;
+    run += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (jsel < 0) jsel = jlast_pos >= 0 ? jlast_pos : n1 - 1;  // rounding at the row's end
+  if (lane == 0) {
+    i_out[draw] = i;
+    j_out[draw] = jsel;
+  }
+}
+
+__global__ void perm_draw_kernel(const int32_t* __restrict__ sigma, const double* __restrict__ stairs,
+                                 int n, const double* __restrict__ uniforms, int n_draws,
+                                 int64_t* __restrict__ i_out, int64_t* __restrict__ j_out) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n_draws) return;
+  const double u = uniforms[d];
+  int lo = 0, hi = n - 1;  // first k with stairs[k] > u  (searchsorted side='right')
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (stairs[mid] > u) hi = mid; else lo = mid + 1;
+  }
+  i_out[d] = lo;
+  j_out[d] = sigma[lo];
+}
+
+template <class E>
+static int sample_common(E ent, int n0, int n1, const double* uniforms, int n_draws, int64_t* i_out,
+                         int64_t* j_out, int32_t* status, void* ws, size_t ws_bytes, cudaStream_t s) {
+  CFM_REQUIRE(ws && ws_bytes >= cfm_plan_sample_workspace_bytes(n0), "plan sample: workspace too small");
+  double* rowmass = reinterpret_cast<double*>(ws);
+  double* rowcdf = rowmass + n0;
+  row_mass_kernel<E><<<(n0 + 7) / 8, 256, 0, s>>>(ent, n0, n1, rowmass, status);
+  row_cdf_kernel<<<1, 1024, 0, s>>>(rowmass, n0, rowcdf, status);
+  if (n_draws > 0)
+    draw_kernel<E><<<(n_draws + 7) / 8, 256, 0, s>>>(ent, n0, n1, rowcdf, uniforms, n_draws, i_out, j_out);
+  CFM_CUDA_OK(cudaGetLastError());
+  return CFM_OK;
+}
+
+}  // namespace cfm
+
+using namespace cfm;
+
+extern "C" size_t cfm_plan_sample_workspace_bytes(int n0) { return ((size_t)2 * n0 + 2) * sizeof(double); }
+
+extern "C" int cfm_plan_sample(const float* M, int n0, int n1, int64_t ldm, float reg,
+                               const float* cost_max, int normalize, const double* log_u,
+                               const double* log_v, const double* uniforms, int n_draws,
+                               int64_t* i_out, int64_t* j_out, int32_t* status, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  CFM_REQUIRE(M && log_u && log_v && (n_draws == 0 || (uniforms && i_out && j_out)),
+              "cfm_plan_sample: null pointer");
+  CFM_REQUIRE(n0 > 0 && n1 > 0 && ldm >= n1 && n_draws >= 0, "cfm_plan_sample: bad shape");
+  CFM_REQUIRE(!(normalize && !cost_max), "cfm_plan_sample: normalize needs cost_max");
+  PotEntry ent{M, ldm, reg, cost_max, normalize, log_u, log_v};
+  return sample_common(ent, n0, n1, uniforms, n_draws, i_out, j_out, status, workspace,
+                       workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int cfm_dense_plan_sample_f64(const double* plan, int n0, int n1, const double* uniforms,
+                                         int n_draws, int64_t* i_out, int64_t* j_out,
+                                         void* workspace, size_t workspace_bytes, void* stream) {
+  CFM_REQUIRE(plan && uniforms && i_out && j_out, "cfm_dense_plan_sample_f64: null pointer");
+  CFM_REQUIRE(n0 > 0 && n1 > 0 && n_draws >= 0, "cfm_dense_plan_sample_f64: bad shape");
+  DenseEntry ent{plan, (int64_t)n1};
+  return sample_common(ent, n0, n1, uniforms, n_draws, i_out, j_out, nullptr, workspace,
+                       workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int cfm_perm_plan_sample(const int32_t* sigma, const double* stairs, int n,
+                                    const double* uniforms, int n_draws, int64_t* i_out,
+                                    int64_t* j_out, void* stream) {
+  CFM_REQUIRE(sigma && stairs && uniforms && i_out && j_out, "cfm_perm_plan_sample: null pointer");
+  CFM_REQUIRE(n > 0 && n_draws >= 0, "cfm_perm_plan_sample: bad shape");
+  if (n_draws == 0) return CFM_OK;
+  perm_draw_kernel<<<(n_draws + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sigma, stairs, n, uniforms,
+                                                                          n_draws, i_out, j_out);
+  CFM_CUDA_OK(cudaGetLastError());
+  return CFM_OK;
+}
+
+extern "C" int cfm_plan_dot_cost(const float* M, int n0, int n1, int64_t ldm, float reg,
+                                 const float* cost_max, int normalize, const double* log_u,
+                                 const double* log_v, double* out, void* stream) {
+  CFM_REQUIRE(M && log_u && log_v && out, "cfm_plan_dot_cost: null pointer");
+  CFM_REQUIRE(n0 > 0 && n1 > 0 && ldm >= n1, "cfm_plan_dot_cost: bad shape");
+  CFM_REQUIRE(!(normalize && !cost_max), "cfm_plan_dot_cost: normalize needs cost_max");
+  cudaStream_t s = (cudaStream_t)stream;
+  CFM_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(double), s));
+  PotEntry ent{M, ldm, reg, cost_max, normalize, log_u, log_v};
+  plan_dot_cost_kernel<<<(n0 + 7) / 8, 256, 0, s>>>(ent, n0, n1, out);
+  CFM_CUDA_OK(cudaGetLastError());
+  return CFM_OK;
+}

@@ -1,0 +1,56 @@
+"""Multi-GPU coupling: minibatch sharding, one process per GPU (torch.distributed).
+
+The reference's only parallelism is data parallelism in which every rank runs its OWN minibatch
+OT on its local ``batch_size // world_size`` shard (examples/images/cifar10/train_cifar10_ddp.py
+:71-77,169): the coupling never crosses ranks.  BASELINE.json's north_star prescribes the same
+partitioning ("coupling stays per-shard, NCCL over NVLink only to gather sampled indices").
+
+``sharded_sample_pairs`` therefore solves the local (N/G x N/G) coupling with the device kernels
+and all-gathers the 2 x N/G int64 global indices (<= 128 KB per rank at N = 64k): a latency-bound
+NCCL all_gather on a side stream, overlappable with the next coupling.  There is no data-path
+collective besides it.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n, world_size, rank):
+    """Contiguous shard [lo, hi) of ``n`` rows for ``rank`` (first n % world_size ranks get +1)."""
+    base, rem = divmod(n, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def sharded_sample_pairs(sampler, x0_local, x1_local, group=None, gather=True, global_offset=None,
+                         pair_fn=None):
+    """Per-shard coupling + optional all-gather of the sampled index pairs.
+
+    x0_local / x1_local: this rank's shard.  Returns (i_local, j_local) device index tensors into
+    the shard and, if ``gather``, also (i_global, j_global): the concatenation over ranks of the
+    pairs offset into the global batch (rank r's rows start at ``global_offset`` = sum of the
+    shard sizes of ranks < r, all-gathered from the shard sizes when not given).
+    ``pair_fn`` (tests only) replaces ``sampler.sample_pairs``.
+    """
+    fn = pair_fn if pair_fn is not None else sampler.sample_pairs
+    i, j = fn(x0_local, x1_local)
+    if not gather or not dist.is_available() or not dist.is_initialized():
+        return (i, j, i, j) if gather else (i, j)
+    ws = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n_local = torch.tensor([x0_local.shape[0]], dtype=torch.int64, device=i.device)
+    sizes = [torch.zeros_like(n_local) for _ in range(ws)]
+    dist.all_gather(sizes, n_local, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    off = sum(sizes[:rank]) if global_offset is None else int(global_offset)
+    pairs = torch.stack([i + off, j + off])  # (2, n_local) int64, global row numbers
+    pad = max(sizes)
+    if pairs.shape[1] != pad:  # ragged shards: pad to the largest so every rank sends equal bytes
+        buf = torch.zeros((2, pad), dtype=pairs.dtype, device=pairs.device)
+        buf[:, :pairs.shape[1]] = pairs
+        pairs = buf
+    outs = [torch.empty_like(pairs) for _ in range(ws)]
+    dist.all_gather(outs, pairs.contiguous(), group=group)
+    chunks = [o[:, :n] for o, n in zip(outs, sizes)]
+    ig = torch.cat([c[0] for c in chunks])
+    jg = torch.cat([c[1] for c in chunks])
+    return i, j, ig, jg

@@ -1,0 +1,147 @@
+"""Lock-step ODE sampling driver: drop-in for the way the reference uses torchdyn,
+
+    node = NeuralODE(torch_wrapper(model), solver="dopri5", sensitivity="adjoint",
+                     atol=1e-4, rtol=1e-4)
+    traj = node.trajectory(x, t_span=torch.linspace(0, 1, 100))
+
+(examples/2D_tutorials/tutorial_training_8_gaussians_to_moons.ipynb:332-338;
+examples/images/mnist_example.ipynb:67,126-128).  torchdyn is an un-vendored dependency
+(setup.py:13); its dopri5 semantics (ONE scalar step for the whole batch, global RMS error norm,
+steps clipped to land on every ``t_span`` entry, Hairer initial step) are restated in
+oracle/vector_field.py and implemented here with the step controller resident on the device
+(csrc/rk.cu): one step = 6 x (stage-input kernel + fused MLP forward) + error norm + control +
+commit, enqueued back to back; the host reads a 64-byte state struct once per step only to learn
+whether the integration has finished.
+
+Only the hot path the north_star names is accelerated: the vector field must be a
+``cfm_b200.models.MLP`` (optionally inside ``torch_wrapper``) on a CUDA device; anything else
+raises -- there is no eager fallback.
+"""
+import ctypes as C
+
+import torch
+
+from . import _ffi
+from .models import MLP, torch_wrapper
+
+
+def _unwrap(vf):
+    m = vf.model if isinstance(vf, torch_wrapper) else vf
+    if not isinstance(m, MLP) or not m.time_varying:
+        raise TypeError("cfm_b200.NeuralODE accelerates cfm_b200.models.MLP(time_varying=True) "
+                        "vector fields (optionally wrapped in torch_wrapper); got "
+                        f"{type(m).__name__}")
+    return m
+
+
+class NeuralODE(torch.nn.Module):
+    """Subset of torchdyn.core.NeuralODE used by the reference examples."""
+
+    def __init__(self, vector_field, solver="dopri5", sensitivity="adjoint", atol=1e-4, rtol=1e-4,
+                 **unused):
+        super().__init__()
+        self.vf = vector_field
+        if solver not in ("dopri5", "euler"):
+            raise NotImplementedError(f"solver {solver!r}: the B200 driver provides 'dopri5' and 'euler'")
+        self.solver, self.atol, self.rtol = solver, float(atol), float(rtol)
+        self.sensitivity = sensitivity  # irrelevant under no_grad sampling; kept for API parity
+        self.stats = {}
+        self.sync_every = 1  # steps enqueued between host reads of the controller state
+
+    @torch.no_grad()
+    def forward(self, x, t_span):
+        traj = self.trajectory(x, t_span)
+        return t_span.to(x.device), traj
+
+    @torch.no_grad()
+    def trajectory(self, x, t_span):
+        mlp = _unwrap(self.vf)
+        if not x.is_cuda:
+            raise _ffi.CfmLibraryError("NeuralODE.trajectory needs CUDA inputs (no CPU fallback)")
+        dev = x.device
+        shape = x.shape
+        x0 = x.detach().reshape(shape[0], -1).float().contiguous()
+        t_span = torch.as_tensor(t_span, dtype=torch.float32)
+        if self.solver == "euler":
+            out = self._euler(mlp, x0, t_span)
+        else:
+            out = self._dopri5(mlp, x0, t_span.to(dev).contiguous())
+        return out.reshape(out.shape[0], *shape)
+
+    # ------------------------------------------------------------------------------------
+    def _euler(self, mlp, x, t_span):
+        L = _ffi.lib()
+        ts = t_span.tolist()
+        numel = x.numel()
+        traj = torch.empty((len(ts),) + tuple(x.shape), dtype=torch.float32, device=x.device)
+        traj[0].copy_(x)
+        k = torch.empty_like(x)
+        for n in range(len(ts) - 1):
+            mlp.vector_field(ts[n], traj[n], out=k)
+            _ffi.check(L.cfm_axpy_f32(_ffi.ptr(traj[n]), _ffi.ptr(k), ts[n + 1] - ts[n],
+                                      _ffi.ptr(traj[n + 1]), numel, _ffi.stream_ptr(x.device)),
+                       "cfm_axpy_f32")
+        self.stats = {"nfe": len(ts) - 1, "accepted": len(ts) - 1, "rejected": 0}
+        return traj
+
+    def _dopri5(self, mlp, x0, t_span):
+        L = _ffi.lib()
+        dev = x0.device
+        B, D = x0.shape
+        numel = x0.numel()
+        n_span = t_span.numel()
+        sp = _ffi.stream_ptr(dev)
+        ts_host = t_span.cpu()
+
+        x = x0.clone()
+        xnew = torch.empty_like(x)
+        xs = torch.empty_like(x)
+        k = torch.empty((7, B, D), dtype=torch.float32, device=dev)
+        traj = torch.empty((n_span, B, D), dtype=torch.float32, device=dev)
+        traj[0].copy_(x)
+        t_stage = torch.zeros(1, dtype=torch.float32, device=dev)
+        scratch = torch.zeros(4, dtype=torch.float64, device=dev)
+
+        st_host = _ffi.RkState()
+        st_host.t, st_host.t_end = float(ts_host[0]), float(ts_host[-1])
+        st_host.atol, st_host.rtol = self.atol, self.rtol
+        st_host.n_span, st_host.ckpt, st_host.save_slot = n_span, 1, -1
+        st_bytes = torch.frombuffer(bytearray(bytes(st_host)), dtype=torch.uint8)
+        st = st_bytes.to(dev)
+        stp = _ffi.ptr(st)
+
+        # k1 = f(t0, x); Hairer initial step needs one extra evaluation
+        mlp.vector_field(st_host.t, x, out=k[0])
+        _ffi.check(L.cfm_rk_init_a(stp, _ffi.ptr(x), _ffi.ptr(k[0]), _ffi.ptr(xs), _ffi.ptr(t_stage),
+                                   _ffi.ptr(scratch), numel, sp), "cfm_rk_init_a")
+        mlp.vector_field(t_stage, xs, out=k[1])
+        _ffi.check(L.cfm_rk_init_b(stp, _ffi.ptr(x), _ffi.ptr(k[0]), _ffi.ptr(k[1]), _ffi.ptr(t_span),
+                                   _ffi.ptr(scratch), numel, sp), "cfm_rk_init_b")
+
+        pinned = torch.empty(st.numel(), dtype=torch.uint8, pin_memory=True)
+        max_steps = 100000
+        steps = 0
+        while steps < max_steps:
+            for _ in range(self.sync_every):
+                for stage in range(1, 7):
+                    out = xs if stage < 6 else xnew
+                    _ffi.check(L.cfm_rk_stage_input(stp, _ffi.ptr(x), _ffi.ptr(k), _ffi.ptr(out),
+                                                    _ffi.ptr(t_stage), numel, stage, sp),
+                               "cfm_rk_stage_input")
+                    mlp.vector_field(t_stage, out, out=k[stage])
+                _ffi.check(L.cfm_rk_error_norm(stp, _ffi.ptr(x), _ffi.ptr(xnew), _ffi.ptr(k), numel, sp),
+                           "cfm_rk_error_norm")
+                _ffi.check(L.cfm_rk_control(stp, _ffi.ptr(t_span), numel, sp), "cfm_rk_control")
+                _ffi.check(L.cfm_rk_commit(stp, _ffi.ptr(x), _ffi.ptr(xnew), _ffi.ptr(k),
+                                           _ffi.ptr(traj), numel, sp), "cfm_rk_commit")
+                steps += 1
+            pinned.copy_(st, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            cur = _ffi.RkState.from_buffer_copy(bytes(pinned.numpy().tobytes()))
+            if cur.done:
+                break
+        else:
+            raise RuntimeError("dopri5: step budget exhausted")
+        self.stats = {"nfe": cur.nfe, "accepted": cur.accepted, "rejected": cur.rejected,
+                      "t": cur.t, "last_ratio": cur.ratio}
+        return traj

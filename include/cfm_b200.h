@@ -1,0 +1,215 @@
+/* cfm_b200.h -- C ABI of libcfm_b200.so (sm_100a kernels for torchcfm's two hot paths).
+ *
+ * The reference (atong01/conditional-flow-matching, torchcfm 1.0.7) is pure Python and
+ * has no FFI of its own; the boundary below is what a binding for its hot path would
+ * have to provide.  Each entry point names the reference interface it replaces
+ * (paths relative to the reference root).  All pointers are DEVICE pointers unless the
+ * name ends in `_host`; sizes are element counts unless stated; every call is
+ * asynchronous on `stream` (a cudaStream_t passed as void*), allocates nothing and
+ * keeps no state besides a per-thread error string.  Return value: 0 = ok, <0 = error
+ * (see CFM_ERR_*; text via cfm_last_error()).  Numerical conditions are reported
+ * through device-resident status words, never through the return value.
+ */
+#ifndef CFM_B200_H_
+#define CFM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CFM_ABI_VERSION 1
+
+#define CFM_OK 0
+#define CFM_ERR_ARG (-1)   /* bad argument (shape, alignment, null pointer, workspace too small) */
+#define CFM_ERR_CUDA (-2)  /* a CUDA runtime call failed */
+#define CFM_ERR_ARCH (-3)  /* device is not sm_100 / kernel image missing */
+
+/* status-word bit flags written by the solvers (device int32) */
+#define CFM_FLAG_NONFINITE 1      /* optimal_transport.py:88-92  "p is not finite"            */
+#define CFM_FLAG_ZERO_MASS 2      /* optimal_transport.py:93-96  uniform-plan fallback taken  */
+#define CFM_FLAG_NOT_CONVERGED 4  /* POT "Sinkhorn did not converge" (numItermax reached)     */
+#define CFM_FLAG_INFEASIBLE 8     /* exact assignment found no augmenting path (inf/nan cost) */
+
+/* activations for cfm_mlp_forward_f32 */
+#define CFM_ACT_SELU 0 /* torchcfm/models/models.py:12,14,16 (the reference MLP) */
+#define CFM_ACT_SILU 1 /* notebook-local MLP2 variant named by BASELINE.json north_star */
+
+/* ---- library ---------------------------------------------------------------- */
+int cfm_abi_version(void);
+const char* cfm_last_error(void);
+/* sm count and compute capability (major*10+minor) of the current device */
+int cfm_device_info(int* sm_count, int* cc);
+
+/* ---- (a3) cost matrix: M = torch.cdist(x0, x1) ** 2 --------------------------
+ * replaces torchcfm/optimal_transport.py:84 (and :176, :297-299).
+ * x0 (n0,d), x1 (n1,d) fp32 row-major contiguous; M (n0, n1) fp32 with row stride ldm.
+ * M_ij = (sqrt(max(|x0_i|^2 + |x1_j|^2 - 2 x0_i.x1_j, 0)))^2 when squared != 0, the
+ * un-squared distance otherwise (wasserstein power=1, :297).
+ * cost_max (nullable, 1 float): receives max_ij M_ij (the M.max() of :86); must be
+ * zeroed by the caller... it is zeroed by this call.
+ * algo: 0 auto, 1 SIMT fp32 FMA, 2 tcgen05 3xTF32 (error-compensated, fp32-grade).
+ */
+size_t cfm_sqdist_workspace_bytes(int n0, int n1, int d, int algo);
+int cfm_sqdist_f32(const float* x0, const float* x1, float* M, int n0, int n1, int d,
+                   int64_t ldm, int squared, float* cost_max, int algo, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* ---- (a4) entropic plan: log-domain Sinkhorn on uniform marginals ---------------
+ * replaces pot.sinkhorn(a, b, M, reg) as bound at optimal_transport.py:51 and called
+ * at :87 (POT algorithm: ot/bregman/_sinkhorn.py::sinkhorn_log; a = b = pot.unif, :79).
+ * M (n0,n1) fp32; if normalize != 0 the cost used is M / *cost_max (:85-86).
+ * Iterates v then u (POT order), at most max_iters times; every `check_every`
+ * iterations (POT: 10) the column-marginal L2 error is tested against stop_thr.
+ * precise: 0 = fp32 exponent arithmetic (|M/reg| <~ 64), 1 = float64 potentials and
+ * IEEE fp32 division for -M/reg exactly as NumPy forms it, -1 = choose on device from
+ * *cost_max / reg.
+ * Outputs: log_u (n0), log_v (n1) float64 natural-log potentials with
+ *   plan_ij = exp(-M_ij/reg + log_u_i + log_v_j);
+ * stall_tol: 0 = POT's stopping rule only.  > 0 additionally stops at a check when the
+ * error improved by less than this fraction since the previous check AND the RMS
+ * relative column-marginal error is already < 1e-5 (fp32 fixed point reached; POT's
+ * float64 loop would keep shaving an error our fp32 exponents cannot resolve).
+ * status: int32[4] = {flags, iterations run, precise mode used, 0};
+ * err: float64[1] last evaluated column-marginal L2 error.
+ */
+size_t cfm_sinkhorn_workspace_bytes(int n0, int n1);
+int cfm_sinkhorn_log_f32(const float* M, int n0, int n1, int64_t ldm, float reg,
+                         const float* cost_max, int normalize, int max_iters,
+                         double stop_thr, int check_every, int precise, double stall_tol,
+                         double* log_u, double* log_v, int32_t* status, double* err,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* materialise the float64 plan (what OTPlanSampler.get_map returns, :63-97) from the
+ * potentials; also accumulates total mass into mass[0] (float64) and sets
+ * CFM_FLAG_NONFINITE in *status when an entry is not finite. */
+int cfm_plan_materialize_f64(const float* M, int n0, int n1, int64_t ldm, float reg,
+                             const float* cost_max, int normalize, const double* log_u,
+                             const double* log_v, double* plan, double* mass,
+                             int32_t* status, void* stream);
+
+/* <P, M> = sum_ij plan_ij * M_ij into out[0] (float64): the value pot.sinkhorn2 returns
+ * (optimal_transport.py:288, called at :300 by wasserstein()). */
+int cfm_plan_dot_cost(const float* M, int n0, int n1, int64_t ldm, float reg,
+                      const float* cost_max, int normalize, const double* log_u,
+                      const double* log_v, double* out, void* stream);
+
+/* ---- (a6) pair sampling ---------------------------------------------------------
+ * replaces OTPlanSampler.sample_map for replace=True (optimal_transport.py:116-121):
+ * inverse-CDF draw over the row-major flattened plan for `n_draws` uniforms in [0,1)
+ * (the caller draws them with np.random.random_sample to keep the reference's RNG
+ * stream), returning row and column indices (int64, like np.divmod).
+ * The plan is never materialised: entries are recomputed from (M, log_u, log_v).
+ * workspace: cfm_plan_sample_workspace_bytes(n0).  If the total mass is < 1e-8 the
+ * uniform plan is sampled instead and CFM_FLAG_ZERO_MASS is set (:93-96).
+ */
+size_t cfm_plan_sample_workspace_bytes(int n0);
+int cfm_plan_sample(const float* M, int n0, int n1, int64_t ldm, float reg,
+                    const float* cost_max, int normalize, const double* log_u,
+                    const double* log_v, const double* uniforms, int n_draws,
+                    int64_t* i_out, int64_t* j_out, int32_t* status, void* workspace,
+                    size_t workspace_bytes, void* stream);
+/* same draw for a dense float64 plan already in device memory (staged parity test) */
+int cfm_dense_plan_sample_f64(const double* plan, int n0, int n1, const double* uniforms,
+                              int n_draws, int64_t* i_out, int64_t* j_out,
+                              void* workspace, size_t workspace_bytes, void* stream);
+/* exact-OT plan P_sigma/N: cdf is the N-step staircase `stairs` (float64, n entries,
+ * the normalised sequential cumsum the reference forms); i = searchsorted(stairs, u,
+ * 'right'), j = sigma[i]. */
+int cfm_perm_plan_sample(const int32_t* sigma, const double* stairs, int n,
+                         const double* uniforms, int n_draws, int64_t* i_out,
+                         int64_t* j_out, void* stream);
+
+/* ---- (a4, exact) optimal assignment on uniform marginals -------------------------
+ * replaces pot.emd(a, b, M) as bound at optimal_transport.py:49 / called at :87, and
+ * scipy.optimize.linear_sum_assignment at :179.  For a = b = 1/n the LP vertex is
+ * P_sigma / n; this returns sigma (column of each row), solved by a shortest-
+ * augmenting-path method in float64 on the fp32 costs (the reference casts M to
+ * float64 too).  total_cost (float64[1]) = sum_i M[i, sigma_i] (emd2 * n, :300).
+ * status: int32[2] = {flags, augmentations}.
+ */
+size_t cfm_assign_workspace_bytes(int n);
+int cfm_assign_exact_f32(const float* M, int n, int64_t ldm, const float* cost_max,
+                         int normalize, int32_t* sigma, double* total_cost,
+                         int32_t* status, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/* ---- (a7) gather: out[k, :] = x[idx[k], :] ---------------------------------------
+ * replaces x0[i], x1[j] at optimal_transport.py:145 / :213-218.  elem_bytes in {1,2,4,8}.
+ */
+int cfm_gather_rows(const void* x, int64_t row_elems, int elem_bytes, const int64_t* idx,
+                    int64_t n_idx, void* out, void* stream);
+
+/* ---- (a9/a10) MLP vector field ----------------------------------------------------
+ * replaces torchcfm.models.MLP.forward (torchcfm/models/models.py:20-21) composed with
+ * torch_wrapper.forward (torchcfm/utils.py:51-52): y = net(cat([x, t], 1)).
+ * x (B, dim) fp32 contiguous.  Weights in torch.nn.Linear layout W_l (out_l, in_l),
+ * b_l (out_l); `in_0 = dim + time_varying`.  When time_varying != 0, t is a scalar
+ * shared by the batch and is folded into the first-layer bias; it is read from
+ * *t_dev (device float) when t_dev != NULL, else t_host is used.
+ * prepared: opaque device blob built once per weight set by cfm_mlp_prepare (split /
+ * padded copies of the weights); workspace holds the two hidden activations.
+ */
+size_t cfm_mlp_prepared_bytes(int dim, int w, int out_dim, int time_varying);
+int cfm_mlp_prepare(const float* W0, const float* b0, const float* W1, const float* b1,
+                    const float* W2, const float* b2, const float* W3, const float* b3,
+                    int dim, int w, int out_dim, int time_varying, void* prepared,
+                    size_t prepared_bytes, void* stream);
+size_t cfm_mlp_workspace_bytes(int batch, int dim, int w, int out_dim, int algo);
+int cfm_mlp_forward_f32(const void* prepared, const float* x, int batch, int dim, int w,
+                        int out_dim, int time_varying, const float* t_dev, float t_host,
+                        int act, float* y, int algo, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* ---- (a11) dopri5 lock-step driver pieces -------------------------------------------
+ * replaces the arithmetic of torchdyn's NeuralODE(solver="dopri5").trajectory (call
+ * sites: examples/2D_tutorials/tutorial_training_8_gaussians_to_moons.ipynb:332-338;
+ * torchdyn >= 1.0.6 is an un-vendored dependency, setup.py:13).  The batch advances in
+ * lock-step with ONE scalar step size, so all step-control state lives in a device
+ * struct and a whole step is enqueued without a host round trip.  Driver:
+ * cfm_b200/ode.py.  Buffers are fp32 with numel = B*D elements: x, xnew, xs and
+ * k = 7 contiguous stage derivatives k1..k7.
+ */
+typedef struct cfm_rk_state {
+  float t, dt, t_end, atol, rtol;
+  float dt_old;          /* step saved when a checkpoint clipped dt (also h0 during init) */
+  float ratio;           /* last error ratio (hairer norm)                                */
+  int32_t ckpt_flag;     /* dt was clipped to land on t_span[ckpt]                         */
+  int32_t ckpt;          /* next t_span index to record                                    */
+  int32_t n_span;        /* len(t_span)                                                    */
+  int32_t commit;        /* last step accepted: cfm_rk_commit applies it                   */
+  int32_t done;          /* t >= t_end                                                     */
+  int32_t save_slot;     /* >= 0: commit also copies the new state into traj[save_slot]    */
+  int32_t accepted, rejected, nfe;
+  double err_acc;        /* sum((err/tol)^2) accumulated by cfm_rk_error_norm              */
+} cfm_rk_state;
+
+/* stage in 1..5: out = x + dt*sum_j a[stage][j]*k_j (input of stage+1's evaluation);
+ * stage 6: the same with the 5th-order weights, i.e. out = xnew (and the FSAL input).
+ * *t_stage (device float, nullable) = t + c[stage]*dt. */
+int cfm_rk_stage_input(const cfm_rk_state* st, const float* x, const float* k, float* out,
+                       float* t_stage, int64_t numel, int stage, void* stream);
+/* st->err_acc += sum((dt*sum_j e_j k_j / (atol + rtol*max(|x|,|xnew|)))^2) */
+int cfm_rk_error_norm(cfm_rk_state* st, const float* x, const float* xnew, const float* k,
+                      int64_t numel, void* stream);
+/* accept/reject, checkpoint bookkeeping, step-size adaptation, clipping of the next dt */
+int cfm_rk_control(cfm_rk_state* st, const float* t_span, int64_t numel, void* stream);
+/* if the step was accepted: x <- xnew, k1 <- k7 (FSAL), traj[save_slot] <- xnew */
+int cfm_rk_commit(const cfm_rk_state* st, float* x, const float* xnew, float* k, float* traj,
+                  int64_t numel, void* stream);
+/* Hairer initial step (torchdyn init_step) around the f(t0+h0, x+h0*f0) evaluation:
+ * init_a writes x_probe and *t_stage; init_b finishes dt and clips it.  scratch: 4 doubles. */
+int cfm_rk_init_a(cfm_rk_state* st, const float* x, const float* f0, float* x_probe,
+                  float* t_stage, double* scratch, int64_t numel, void* stream);
+int cfm_rk_init_b(cfm_rk_state* st, const float* x, const float* f0, const float* f1,
+                  const float* t_span, double* scratch, int64_t numel, void* stream);
+/* x_out = x + h * k  (fixed-step Euler, torchdyn solver="euler") */
+int cfm_axpy_f32(const float* x, const float* k, float h, float* x_out, int64_t numel,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFM_B200_H_ */

@@ -1,0 +1,204 @@
+"""Host-side logic that needs no GPU: API surface parity with the reference, error behaviour,
+the non-OT matchers (pure elementwise torch) against the golden vectors, NumPy-contract sampling,
+shard arithmetic and the world_size-2 gloo path of the index all-gather."""
+import inspect
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import cfm_b200
+from cfm_b200 import dist as cdist
+from cfm_b200.optimal_transport import OTPlanSampler, wasserstein
+from conftest import REFERENCE, ROOT
+
+
+def test_ctor_contract():
+    s = OTPlanSampler("sinkhorn", reg=0.3, reg_m=2.0, normalize_cost=True, num_threads="max", warn=False)
+    assert (s.reg, s.reg_m, s.normalize_cost, s.warn) == (0.3, 2.0, True, False)
+    assert callable(s.ot_fn)
+    with pytest.raises(ValueError, match="Unknown method: nope"):
+        OTPlanSampler("nope")
+    for m in ("unbalanced", "partial"):  # accepted like the reference; solving is out of scope
+        with pytest.raises(NotImplementedError):
+            OTPlanSampler(m).ot_fn(None, None, None)
+    with pytest.raises(ValueError):
+        wasserstein(torch.zeros(2, 2), torch.zeros(2, 2), "noname")
+    with pytest.raises(ValueError):
+        cfm_b200.SchrodingerBridgeConditionalFlowMatcher(sigma=0.0)
+    with pytest.warns(UserWarning):
+        cfm_b200.SchrodingerBridgeConditionalFlowMatcher(sigma=1e-4)
+    fm = cfm_b200.SchrodingerBridgeConditionalFlowMatcher(sigma=0.5, ot_method="sinkhorn")
+    assert fm.ot_method == "sinkhorn" and fm.ot_sampler.reg == 2 * 0.5**2
+    assert cfm_b200.ExactOptimalTransportConditionalFlowMatcher().ot_sampler.method == "exact"
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference tree not mounted (GPU box)")
+def test_signatures_match_reference_source():
+    """Compare public signatures with the reference *source* (parsed, not imported)."""
+    import ast
+    def sigs(path, classes):
+        tree = ast.parse(open(path).read())
+        out = {}
+        for node in tree.body:
+            if isinstance(node, ast.ClassDef) and node.name in classes:
+                for fn in node.body:
+                    if isinstance(fn, ast.FunctionDef) and (not fn.name.startswith("_") or fn.name == "__init__"):
+                        out[(node.name, fn.name)] = [a.arg for a in fn.args.args]
+            if isinstance(node, ast.FunctionDef) and not node.name.startswith("_"):
+                out[("", node.name)] = [a.arg for a in node.args.args]
+        return out
+    ref = sigs(f"{REFERENCE}/torchcfm/optimal_transport.py", {"OTPlanSampler"})
+    ref.update(sigs(f"{REFERENCE}/torchcfm/conditional_flow_matching.py", {
+        "ConditionalFlowMatcher", "ExactOptimalTransportConditionalFlowMatcher",
+        "TargetConditionalFlowMatcher", "SchrodingerBridgeConditionalFlowMatcher",
+        "VariancePreservingConditionalFlowMatcher"}))
+    ref.update(sigs(f"{REFERENCE}/torchcfm/models/models.py", {"MLP"}))
+    import cfm_b200.conditional_flow_matching as m_cfm
+    import cfm_b200.models as m_models
+    import cfm_b200.optimal_transport as m_ot
+    for (cls, fn), args in ref.items():
+        if cls == "":
+            mod = m_ot if hasattr(m_ot, fn) else m_cfm
+            obj = getattr(mod, fn)
+        else:
+            owner = next(getattr(m, cls) for m in (m_ot, m_cfm, m_models) if hasattr(m, cls))
+            obj = getattr(owner, fn)
+        mine = [p for p, v in inspect.signature(obj).parameters.items()
+                if v.kind in (v.POSITIONAL_ONLY, v.POSITIONAL_OR_KEYWORD)]
+        if cls and "self" not in mine:
+            mine = ["self"] + mine
+        assert mine == args, (cls, fn, mine, args)
+
+
+@pytest.mark.parametrize("kind,cls", [("i_cfm", "ConditionalFlowMatcher"),
+                                      ("t_cfm", "TargetConditionalFlowMatcher"),
+                                      ("vp_cfm", "VariancePreservingConditionalFlowMatcher")])
+def test_non_ot_matchers_bit_exact_vs_reference_vectors(golden, kind, cls):
+    fm = getattr(cfm_b200, cls)(0.5)
+    x0, x1 = torch.from_numpy(golden["fm_x0"]), torch.from_numpy(golden["fm_x1"])
+    torch.manual_seed(1994)
+    t, xt, ut, eps = fm.sample_location_and_conditional_flow(x0, x1, return_noise=True)
+    for name, val in (("t", t), ("xt", xt), ("ut", ut), ("eps", eps)):
+        assert torch.equal(val, torch.from_numpy(golden[f"fm_{kind}_{name}"])), name
+    np.testing.assert_array_equal(np.asarray(fm.compute_lambda(t)), golden[f"fm_{kind}_lambda"])
+    t2, *_ = fm.sample_location_and_conditional_flow(x0, x1, t=t)
+    assert t2 is t
+    with pytest.raises(AssertionError):
+        fm.sample_location_and_conditional_flow(x0, x1, t=t[:5])
+
+
+def test_pad_t_like_x():
+    x = torch.zeros(7, 2, 3, 4)
+    assert cfm_b200.pad_t_like_x(torch.arange(7.0), x).shape == (7, 1, 1, 1)
+    assert cfm_b200.pad_t_like_x(0.3, x) == 0.3 and cfm_b200.pad_t_like_x(2, x) == 2
+
+
+def test_sample_map_numpy_contract():
+    """reference tests/test_optimal_transport.py:15-29: a permutation plan drawn without
+    replacement returns every entry exactly once; with replacement it follows np.random.choice."""
+    s = OTPlanSampler("exact")
+    n = 128
+    perm = np.random.default_rng(0).permutation(np.eye(n), axis=1)
+    i, j = s.sample_map(perm, batch_size=n, replace=False)
+    rec = np.zeros((n, n))
+    rec[i, j] = 1
+    assert np.array_equal(rec, perm)
+    pi = np.random.default_rng(1).random((16, 24))
+    np.random.seed(4)
+    i, j = s.sample_map(pi, 50)
+    np.random.seed(4)
+    k = np.random.choice(pi.size, p=pi.flatten() / pi.sum(), size=50)
+    assert np.array_equal(i, k // 24) and np.array_equal(j, k % 24)
+
+
+def test_mlp_state_dict_and_cpu_autograd_path():
+    m = cfm_b200.MLP(dim=2, time_varying=True, w=64)
+    assert list(m.state_dict()) == [f"net.{i}.{p}" for i in (0, 2, 4, 6) for p in ("weight", "bias")]
+    assert m.net[0].in_features == 3 and isinstance(m.net[1], torch.nn.SELU)
+    y = m(torch.randn(5, 3))
+    y.sum().backward()  # training path stays a plain nn.Sequential
+    assert m.net[0].weight.grad is not None
+    w = cfm_b200.torch_wrapper(m)
+    assert w.model is m and w(torch.tensor(0.3), torch.randn(5, 2)).shape == (5, 2)
+    with pytest.raises(TypeError):
+        cfm_b200.NeuralODE(torch.nn.Linear(2, 2)).trajectory(torch.zeros(1, 2), torch.linspace(0, 1, 2))
+
+
+def test_hot_path_refuses_to_run_without_a_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from cfm_b200._ffi import CfmLibraryError
+    with pytest.raises(CfmLibraryError):
+        OTPlanSampler("exact").sample_plan(torch.randn(8, 2), torch.randn(8, 2))
+    m = cfm_b200.MLP(dim=2, time_varying=True)
+    with pytest.raises(CfmLibraryError):
+        cfm_b200.NeuralODE(cfm_b200.torch_wrapper(m)).trajectory(torch.zeros(4, 2), torch.linspace(0, 1, 2))
+
+
+def test_compat_alias():
+    import cfm_b200.compat as compat
+    saved = {k: v for k, v in sys.modules.items() if k.split(".")[0] in ("torchcfm", "torchdyn")}
+    try:
+        compat.install_as_torchcfm()
+        from torchcfm.conditional_flow_matching import ExactOptimalTransportConditionalFlowMatcher as E
+        from torchcfm.models import MLP
+        from torchcfm.optimal_transport import OTPlanSampler as O
+        from torchcfm.utils import torch_wrapper  # noqa: F401
+        from torchdyn.core import NeuralODE
+        assert E is cfm_b200.ExactOptimalTransportConditionalFlowMatcher and O is OTPlanSampler
+        assert MLP is cfm_b200.MLP and NeuralODE is cfm_b200.NeuralODE
+    finally:
+        for k in [k for k in sys.modules if k.split(".")[0] in ("torchcfm", "torchdyn")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def test_shard_bounds_partition():
+    for n, ws in ((16384, 4), (8192, 8), (10, 3), (5, 8)):
+        cuts = [cdist.shard_bounds(n, ws, r) for r in range(ws)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+        assert max(h - l for l, h in cuts) - min(h - l for l, h in cuts) <= 1
+
+
+def _gloo_worker(rank, world, port, n_local, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sizes = n_local if isinstance(n_local, (list, tuple)) else [n_local] * world
+        n = sizes[rank]
+        x0, x1 = torch.zeros(n, 3), torch.zeros(n, 3)
+
+        def fake_pairs(a, b):  # deterministic stand-in for the device coupling
+            idx = torch.arange(a.shape[0])
+            return idx, (idx * 7 + rank) % a.shape[0]
+
+        i, j, ig, jg = cdist.sharded_sample_pairs(None, x0, x1, pair_fn=fake_pairs)
+        q.put((rank, i.tolist(), j.tolist(), ig.tolist(), jg.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("sizes", [[6, 6], [5, 3]])
+def test_sharded_pairs_gloo_world2(sizes):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + len(sizes) + sizes[1]
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, sizes, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    want_i, want_j, off = [], [], 0
+    for r, n in enumerate(sizes):
+        want_i += [off + k for k in range(n)]
+        want_j += [off + (k * 7 + r) % n for k in range(n)]
+        off += n
+    for rank, i, j, ig, jg in res:
+        assert i == list(range(sizes[rank]))
+        assert ig == want_i and jg == want_j
