@@ -38,6 +38,7 @@ SIGNATURES = {
     "cfm_abi_version": (_i, []),
     "cfm_last_error": (C.c_char_p, []),
     "cfm_device_info": (_i, [C.POINTER(_i), C.POINTER(_i)]),
+    "cfm_launch_count": (C.c_longlong, []),
     "cfm_sqdist_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "cfm_sqdist_f32": (_i, [_p, _p, _p, _i, _i, _i, _i64, _i, _p, _i, _p, _sz, _p]),
     "cfm_sinkhorn_workspace_bytes": (_sz, [_i, _i]),

@@ -1,6 +1,8 @@
 // Library-level entry points and the error/devinfo plumbing shared by every kernel file.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace cfm {
@@ -13,6 +15,9 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void note_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 struct DevInfo { int dev = -1, sms = 0, cc = 0; };
 static thread_local DevInfo g_dev;
@@ -31,6 +36,7 @@ int cc_major_minor() { refresh_dev(); return g_dev.cc; }
 
 }  // namespace cfm
 
+extern "C" long long cfm_launch_count(void) { return cfm::g_launches.load(); }
 extern "C" int cfm_abi_version(void) { return CFM_ABI_VERSION; }
 extern "C" const char* cfm_last_error(void) { return cfm::g_err; }
 extern "C" int cfm_device_info(int* sm_count, int* cc) {

@@ -258,7 +258,7 @@ extern "C" int cfm_assign_exact_f32(const float* M, int n, int64_t ldm, const fl
   int threads = ((n + 31) / 32) * 32;
   if (threads < 64) threads = 64;
   if (threads > kAsgMaxThreads) threads = kAsgMaxThreads;
-  assign_kernel<<<1, threads, dyn, s>>>(p);
+  assign_kernel<<<1, threads, dyn, s>>>(p); ::cfm::note_launches(1);
   CFM_CUDA_OK(cudaGetLastError());
   return CFM_OK;
 }

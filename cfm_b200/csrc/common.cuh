@@ -30,6 +30,7 @@ void set_error(const char* fmt, ...);
     }                                                                             \
   } while (0)
 
+void note_launches(int n);  // bumps the process-wide kernel-launch counter (cfm_launch_count)
 int sm_count();             // cached cudaDevAttrMultiProcessorCount of the current device
 int cc_major_minor();       // major*10+minor of the current device
 

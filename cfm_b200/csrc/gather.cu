@@ -27,7 +27,7 @@ static cudaError_t launch_gather(const void* x, int64_t words, const int64_t* id
   const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   gather_rows_kernel<W><<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const W*>(x), words, idx,
-                                                         n_idx, reinterpret_cast<W*>(out));
+                                                         n_idx, reinterpret_cast<W*>(out)); ::cfm::note_launches(1);
   return cudaGetLastError();
 }
 

@@ -120,7 +120,7 @@ extern "C" int cfm_mlp_prepare(const float* W0, const float* b0, const float* W1
   CFM_CUDA_OK(cudaMemcpyAsync(B, &h, sizeof(h), cudaMemcpyHostToDevice, s));
   const int in0 = dim + (time_varying ? 1 : 0);
   mlp_split_w0_kernel<<<w, 256, 0, s>>>(W0, w, dim, in0, h.dimp, reinterpret_cast<float*>(B + h.off_w0x),
-                                        reinterpret_cast<float*>(B + h.off_w0t));
+                                        reinterpret_cast<float*>(B + h.off_w0t)); ::cfm::note_launches(1);
   CFM_CUDA_OK(cudaGetLastError());
   auto cp = [&](int64_t off, const float* src, size_t n) {
     return cudaMemcpyAsync(B + off, src, n * 4, cudaMemcpyDeviceToDevice, s);

@@ -259,27 +259,27 @@ extern "C" int cfm_rk_stage_input(const cfm_rk_state* st, const float* x, const 
                                   float* t_stage, int64_t numel, int stage, void* stream) {
   RK_CHECK(st && x && k && out && numel > 0 && stage >= 1 && stage <= 6);
   RK_CHECK(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(out)) & 15) == 0);
-  rk_stage_input_kernel<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(st, x, k, out, t_stage, numel, stage);
+  rk_stage_input_kernel<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(st, x, k, out, t_stage, numel, stage); ::cfm::note_launches(1);
   CFM_CUDA_OK(cudaGetLastError());
   return CFM_OK;
 }
 extern "C" int cfm_rk_error_norm(cfm_rk_state* st, const float* x, const float* xnew, const float* k,
                                  int64_t numel, void* stream) {
   RK_CHECK(st && x && xnew && k && numel > 0);
-  rk_error_norm_kernel<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(st, x, xnew, k, numel);
+  rk_error_norm_kernel<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(st, x, xnew, k, numel); ::cfm::note_launches(1);
   CFM_CUDA_OK(cudaGetLastError());
   return CFM_OK;
 }
 extern "C" int cfm_rk_control(cfm_rk_state* st, const float* t_span, int64_t numel, void* stream) {
   RK_CHECK(st && t_span && numel > 0);
-  rk_control_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(st, t_span, numel);
+  rk_control_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(st, t_span, numel); ::cfm::note_launches(1);
   CFM_CUDA_OK(cudaGetLastError());
   return CFM_OK;
 }
 extern "C" int cfm_rk_commit(const cfm_rk_state* st, float* x, const float* xnew, float* k, float* traj,
                              int64_t numel, void* stream) {
   RK_CHECK(st && x && xnew && k && traj && numel > 0);
-  rk_commit_kernel<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(st, x, xnew, k, traj, numel);
+  rk_commit_kernel<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(st, x, xnew, k, traj, numel); ::cfm::note_launches(1);
   CFM_CUDA_OK(cudaGetLastError());
   return CFM_OK;
 }
@@ -288,8 +288,8 @@ extern "C" int cfm_rk_init_a(cfm_rk_state* st, const float* x, const float* f0, 
   RK_CHECK(st && x && f0 && x_probe && scratch && numel > 0);
   cudaStream_t s = (cudaStream_t)stream;
   CFM_CUDA_OK(cudaMemsetAsync(scratch, 0, 4 * sizeof(double), s));
-  rk_init_reduce_a<<<ew_grid(numel), 256, 0, s>>>(st, x, f0, scratch, numel);
-  rk_init_probe<<<ew_grid(numel), 256, 0, s>>>(st, x, f0, x_probe, t_stage, scratch, numel);
+  rk_init_reduce_a<<<ew_grid(numel), 256, 0, s>>>(st, x, f0, scratch, numel); ::cfm::note_launches(1);
+  rk_init_probe<<<ew_grid(numel), 256, 0, s>>>(st, x, f0, x_probe, t_stage, scratch, numel); ::cfm::note_launches(1);
   CFM_CUDA_OK(cudaGetLastError());
   return CFM_OK;
 }
@@ -297,15 +297,15 @@ extern "C" int cfm_rk_init_b(cfm_rk_state* st, const float* x, const float* f0, 
                              const float* t_span, double* scratch, int64_t numel, void* stream) {
   RK_CHECK(st && x && f0 && f1 && t_span && scratch && numel > 0);
   cudaStream_t s = (cudaStream_t)stream;
-  rk_init_reduce_b<<<ew_grid(numel), 256, 0, s>>>(st, x, f0, f1, scratch, numel);
-  rk_init_finish<<<1, 1, 0, s>>>(st, t_span, scratch, numel);
+  rk_init_reduce_b<<<ew_grid(numel), 256, 0, s>>>(st, x, f0, f1, scratch, numel); ::cfm::note_launches(1);
+  rk_init_finish<<<1, 1, 0, s>>>(st, t_span, scratch, numel); ::cfm::note_launches(1);
   CFM_CUDA_OK(cudaGetLastError());
   return CFM_OK;
 }
 extern "C" int cfm_axpy_f32(const float* x, const float* k, float h, float* x_out, int64_t numel,
                             void* stream) {
   RK_CHECK(x && k && x_out && numel > 0);
-  axpy_kernel<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(x, k, h, x_out, numel);
+  axpy_kernel<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(x, k, h, x_out, numel); ::cfm::note_launches(1);
   CFM_CUDA_OK(cudaGetLastError());
   return CFM_OK;
 }

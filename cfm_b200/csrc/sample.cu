@@ -180,10 +180,10 @@ static int sample_common(E ent, int n0, int n1, const double* uniforms, int n_dr
   CFM_REQUIRE(ws && ws_bytes >= cfm_plan_sample_workspace_bytes(n0), "plan sample: workspace too small");
   double* rowmass = reinterpret_cast<double*>(ws);
   double* rowcdf = rowmass + n0;
-  row_mass_kernel<E><<<(n0 + 7) / 8, 256, 0, s>>>(ent, n0, n1, rowmass, status);
-  row_cdf_kernel<<<1, 1024, 0, s>>>(rowmass, n0, rowcdf, status);
+  row_mass_kernel<E><<<(n0 + 7) / 8, 256, 0, s>>>(ent, n0, n1, rowmass, status); ::cfm::note_launches(1);
+  row_cdf_kernel<<<1, 1024, 0, s>>>(rowmass, n0, rowcdf, status); ::cfm::note_launches(1);
   if (n_draws > 0)
-    draw_kernel<E><<<(n_draws + 7) / 8, 256, 0, s>>>(ent, n0, n1, rowcdf, uniforms, n_draws, i_out, j_out);
+    draw_kernel<E><<<(n_draws + 7) / 8, 256, 0, s>>>(ent, n0, n1, rowcdf, uniforms, n_draws, i_out, j_out); ::cfm::note_launches(1);
   CFM_CUDA_OK(cudaGetLastError());
   return CFM_OK;
 }
@@ -225,7 +225,7 @@ extern "C" int cfm_perm_plan_sample(const int32_t* sigma, const double* stairs, 
   CFM_REQUIRE(n > 0 && n_draws >= 0, "cfm_perm_plan_sample: bad shape");
   if (n_draws == 0) return CFM_OK;
   perm_draw_kernel<<<(n_draws + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sigma, stairs, n, uniforms,
-                                                                          n_draws, i_out, j_out);
+                                                                          n_draws, i_out, j_out); ::cfm::note_launches(1);
   CFM_CUDA_OK(cudaGetLastError());
   return CFM_OK;
 }
@@ -239,7 +239,7 @@ extern "C" int cfm_plan_dot_cost(const float* M, int n0, int n1, int64_t ldm, fl
   cudaStream_t s = (cudaStream_t)stream;
   CFM_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(double), s));
   PotEntry ent{M, ldm, reg, cost_max, normalize, log_u, log_v};
-  plan_dot_cost_kernel<<<(n0 + 7) / 8, 256, 0, s>>>(ent, n0, n1, out);
+  plan_dot_cost_kernel<<<(n0 + 7) / 8, 256, 0, s>>>(ent, n0, n1, out); ::cfm::note_launches(1);
   CFM_CUDA_OK(cudaGetLastError());
   return CFM_OK;
 }

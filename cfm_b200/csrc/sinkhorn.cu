@@ -492,6 +492,7 @@ static int sk_launch(SkParams& p, size_t smem, void* workspace, cudaStream_t s) 
   p.err_ring = reinterpret_cast<double*>(w + L.ring);
   void* args[] = {(void*)&p};
   CFM_CUDA_OK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(kSkThreads), args, smem, s));
+  note_launches(1);
   return CFM_OK;
 }
 
@@ -546,7 +547,7 @@ extern "C" int cfm_plan_materialize_f64(const float* M, int n0, int n1, int64_t 
   CFM_CUDA_OK(cudaMemsetAsync(mass, 0, sizeof(double), s));
   dim3 grid((n1 + 1023) / 1024 > 8 ? 8 : (n1 + 1023) / 1024, n0);
   plan_materialize_kernel<<<grid, 256, 0, s>>>(M, n0, n1, ldm, reg, cost_max, normalize, log_u, log_v,
-                                              plan, mass, status);
+                                              plan, mass, status); ::cfm::note_launches(1);
   CFM_CUDA_OK(cudaGetLastError());
   return CFM_OK;
 }

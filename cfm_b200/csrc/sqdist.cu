@@ -104,8 +104,8 @@ extern "C" int cfm_sqdist_f32(const float* x0, const float* x1, float* M, int n0
   void* tcws = reinterpret_cast<char*>(workspace) + norms_bytes(n0, n1);
 
   if (cost_max) CFM_CUDA_OK(cudaMemsetAsync(cost_max, 0, sizeof(float), s));
-  row_sqnorm_kernel<<<(n0 + 7) / 8, 256, 0, s>>>(x0, n0, d, nx);
-  row_sqnorm_kernel<<<(n1 + 7) / 8, 256, 0, s>>>(x1, n1, d, ny);
+  row_sqnorm_kernel<<<(n0 + 7) / 8, 256, 0, s>>>(x0, n0, d, nx); ::cfm::note_launches(1);
+  row_sqnorm_kernel<<<(n1 + 7) / 8, 256, 0, s>>>(x1, n1, d, ny); ::cfm::note_launches(1);
   CFM_CUDA_OK(cudaGetLastError());
   if (use_tc) {
     return sqdist_tc_launch(x0, x1, M, n0, n1, d, ldm, squared, cost_max, nx, ny, tcws,

@@ -54,3 +54,10 @@ def sharded_sample_pairs(sampler, x0_local, x1_local, group=None, gather=True, g
     ig = torch.cat([c[0] for c in chunks])
     jg = torch.cat([c[1] for c in chunks])
     return i, j, ig, jg
+
+
+def sharded_sample_plan(sampler, x0_local, x1_local, group=None):
+    """Per-shard ``sample_plan`` (what every DDP rank of the reference does) plus the all-gather of
+    the global index pairs.  Returns (x0_local[i], x1_local[j], i_global, j_global)."""
+    i, j, ig, jg = sharded_sample_pairs(sampler, x0_local, x1_local, group=group, gather=True)
+    return sampler._gather(x0_local, i), sampler._gather(x1_local, j), ig, jg

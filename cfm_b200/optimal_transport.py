@@ -59,6 +59,24 @@ class _Coupling:
                  "total_cost", "reg", "normalize", "method", "x0_dev", "x1_dev")
 
 
+class _StageTimer:
+    def __init__(self, sink, stage, device):
+        self.sink, self.stage, self.device = sink, stage, device
+
+    def __enter__(self):
+        if self.sink is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record(torch.cuda.current_stream(self.device))
+        return self
+
+    def __exit__(self, *exc):
+        if self.sink is not None:
+            self.b.record(torch.cuda.current_stream(self.device))
+            self.sink.append((self.stage, self.a, self.b))
+        return False
+
+
 class OTPlanSampler:
     """OTPlanSampler implements sampling coordinates according to an OT plan (wrt squared
     Euclidean cost) with different implementations of the plan calculation.
@@ -109,6 +127,11 @@ class OTPlanSampler:
         self.stall_tol = float(stall_tol)
         self.cost_algo = int(cost_algo)
         self.last_info = {}
+        self.stage_events = None  # set to a list to collect (stage, start_event, end_event)
+
+    def _timed(self, stage, device):
+        """Context manager recording CUDA events around a stage when profiling is on."""
+        return _StageTimer(self.stage_events, stage, device)
 
     # ------------------------------------------------------------------ device stages
     def _cost(self, x0, x1, device, squared=True):
@@ -173,11 +196,14 @@ class OTPlanSampler:
 
     def _couple(self, x0, x1, device):
         """cost + solve on the device; nothing is synchronised or copied to the host."""
-        Mbuf, cmax, n0, n1 = self._cost(x0, x1, device)
+        with self._timed("cost", device):
+            Mbuf, cmax, n0, n1 = self._cost(x0, x1, device)
         if self.method == "exact":
-            cp = self._solve_exact(Mbuf, cmax, n0, n1, self.normalize_cost)
+            with self._timed("solve", device):
+                cp = self._solve_exact(Mbuf, cmax, n0, n1, self.normalize_cost)
         elif self.method == "sinkhorn":
-            cp = self._solve_sinkhorn(Mbuf, cmax, n0, n1, self.reg, self.normalize_cost)
+            with self._timed("solve", device):
+                cp = self._solve_sinkhorn(Mbuf, cmax, n0, n1, self.reg, self.normalize_cost)
         else:
             self._ot_fn_unsupported(None, None, None, method=self.method)
         cp.x0_dev, cp.x1_dev = self._last_inputs  # device fp32 copies made for the cost kernel
@@ -326,9 +352,11 @@ class OTPlanSampler:
             return x0[i], x1[j]
         device = _pick_device(x0, x1)
         cp = self._couple(x0, x1, device)
-        i, j = self._draw(cp, x0.shape[0])
-        out0 = self._gather_like_input(x0, cp.x0_dev, i)
-        out1 = self._gather_like_input(x1, cp.x1_dev, j)
+        with self._timed("draw", device):
+            i, j = self._draw(cp, x0.shape[0])
+        with self._timed("gather", device):
+            out0 = self._gather_like_input(x0, cp.x0_dev, i)
+            out1 = self._gather_like_input(x1, cp.x1_dev, j)
         if self.warn:
             self._report(cp)
         return out0, out1

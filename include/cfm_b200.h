@@ -42,6 +42,8 @@ int cfm_abi_version(void);
 const char* cfm_last_error(void);
 /* sm count and compute capability (major*10+minor) of the current device */
 int cfm_device_info(int* sm_count, int* cc);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+long long cfm_launch_count(void);
 
 /* ---- (a3) cost matrix: M = torch.cdist(x0, x1) ** 2 --------------------------
  * replaces torchcfm/optimal_transport.py:84 (and :176, :297-299).
