@@ -22,104 +22,9 @@
 //   * two arithmetic modes chosen on the device: fast (fp32 log2-domain, one FFMA + one ex2 per
 //     element) and precise (float64 potentials, IEEE fp32 division forming -M/reg exactly as
 //     NumPy does, for |M/reg| >> 64 where fp32 exponents lose the answer).
-#include <cooperative_groups.h>
-
-#include "common.cuh"
-
-namespace cg = cooperative_groups;
+#include "sinkhorn_common.cuh"
 
 namespace cfm {
-
-constexpr int kSkThreads = 512;
-constexpr int kSkWarps = kSkThreads / 32;
-constexpr int kSkChunk = kSkWarps;  // rows per chunk: one warp per row in the row phase
-constexpr int kSkMaxKG = 4;         // column groups (float4) per thread per panel
-constexpr int kPanelCols = kSkThreads * 4 * kSkMaxKG;  // 8192
-
-struct SkParams {
-  const float* M;
-  int n0, n1;
-  int64_t ldm;
-  float reg;
-  const float* cost_max;
-  int normalize;
-  int max_iters;
-  double stop_thr;
-  int check_every;
-  int precise;      // 0 fast, 1 precise, -1 auto
-  double stall_tol; // <=0: off.  else stop when a check improves err by less than this fraction
-  double* log_u;
-  double* log_v;
-  int32_t* status;
-  double* err_out;
-  // workspace
-  void* u_work;     // n0  pot_t
-  void* v_work[2];  // n1p pot_t each
-  void* part_m;     // grid * n1p pot_t
-  float* part_s;    // grid * n1p
-  double* err_ring; // 4
-  int n1p;          // n1 rounded up to a multiple of 4
-  int vec;          // float4 path usable
-  int v_in_smem;
-};
-
-template <bool P> struct Tr;
-template <> struct Tr<false> {
-  using pot_t = float;
-  __device__ static __forceinline__ float init() { return -1.0e30f; }
-};
-template <> struct Tr<true> {
-  using pot_t = double;
-  __device__ static __forceinline__ double init() { return -1.0e300; }
-};
-
-// exponent of one plan entry given the cost entry and the opposite-side potential
-template <bool P> struct Xf;
-template <> struct Xf<false> {  // log2 units: x = M * (-log2e/(reg*scale)) + p2
-  float c2;
-  __device__ __forceinline__ float operator()(float m, float p) const { return fmaf(m, c2, p); }
-};
-template <> struct Xf<true> {  // natural-log units, NumPy's fp32 rounding of -M/reg, f64 add
-  float reg, cmax;
-  int norm;
-  __device__ __forceinline__ double operator()(float m, double p) const {
-    const float mn = norm ? __fdiv_rn(m, cmax) : m;
-    return (double)(-__fdiv_rn(mn, reg)) + p;
-  }
-};
-__device__ __forceinline__ float expdiff(float x, float m) { return ex2f(x - m); }
-__device__ __forceinline__ float expdiff(double x, double m) {
-  return ex2f((float)(x - m) * kLog2e);
-}
-__device__ __forceinline__ float lse_fin(float m, float s) { return m + log2f(s); }
-__device__ __forceinline__ double lse_fin(double m, float s) { return m + log((double)s); }
-__device__ __forceinline__ float vmax(float a, float b) { return fmaxf(a, b); }
-__device__ __forceinline__ double vmax(double a, double b) { return fmax(a, b); }
-
-// load 4 consecutive cost entries of a row starting at column j (pad +inf => zero weight)
-template <bool VEC>
-__device__ __forceinline__ float4 load_cost4(const float* __restrict__ row, int j, int n1) {
-  if (VEC) return ldg_stream4(row + j);
-  float4 r;
-  const float inf = __int_as_float(0x7f800000);
-  r.x = (j + 0 < n1) ? __ldg(row + j + 0) : inf;
-  r.y = (j + 1 < n1) ? __ldg(row + j + 1) : inf;
-  r.z = (j + 2 < n1) ? __ldg(row + j + 2) : inf;
-  r.w = (j + 3 < n1) ? __ldg(row + j + 3) : inf;
-  return r;
-}
-
-template <class T> struct Vec4 { T x, y, z, w; };
-
-// potentials are rewritten during the kernel by other CTAs: read them either from the smem
-// stage (SM) or through ld.global.cg (L2, coherent), never through L1 / the .nc path.
-template <bool SM, class T>
-__device__ __forceinline__ Vec4<T> load_pot4(const T* p, int j) {  // p padded to n1p
-  Vec4<T> r;
-  if (SM) { r.x = p[j]; r.y = p[j + 1]; r.z = p[j + 2]; r.w = p[j + 3]; }
-  else { r.x = __ldcg(p + j); r.y = __ldcg(p + j + 1); r.z = __ldcg(p + j + 2); r.w = __ldcg(p + j + 3); }
-  return r;
-}
 
 // ---- row phase: one warp computes LSE_j(x(M_rj, v_j)) for one row ---------------------------
 template <bool P, bool VEC, bool SM>
@@ -128,8 +33,9 @@ __device__ __forceinline__ typename Tr<P>::pot_t row_lse(const float* __restrict
                                                          int n1, int ng,
                                                          const Xf<P>& xf, int lane) {
   using pot_t = typename Tr<P>::pot_t;
+  using sum_t = typename Tr<P>::sum_t;
   pot_t m = Tr<P>::init();
-  float s = 0.f;
+  sum_t s = 0;
   constexpr int U = P ? 4 : 8;
   for (int g0 = 0; g0 < ng; g0 += 32 * U) {
     float4 c[U];
@@ -154,7 +60,7 @@ __device__ __forceinline__ typename Tr<P>::pot_t row_lse(const float* __restrict
       x[q][2] = xf(c[q].z, pv[q].z); x[q][3] = xf(c[q].w, pv[q].w);
       bm = vmax(bm, vmax(vmax(x[q][0], x[q][1]), vmax(x[q][2], x[q][3])));
     }
-    float acc = s * expdiff(m, bm);
+    sum_t acc = s * expdiff(m, bm);
 #pragma unroll
     for (int q = 0; q < U; ++q)
       acc += (expdiff(x[q][0], bm) + expdiff(x[q][1], bm)) +
@@ -164,7 +70,7 @@ __device__ __forceinline__ typename Tr<P>::pot_t row_lse(const float* __restrict
   }
   // warp combine of (m, s)
   pot_t wm = warp_max(m);
-  float ws = warp_sum(s * expdiff(m, wm));
+  sum_t ws = warp_sum(s * expdiff(m, wm));
   return lse_fin(wm, ws);
 }
 
@@ -172,6 +78,7 @@ __device__ __forceinline__ typename Tr<P>::pot_t row_lse(const float* __restrict
 template <bool P, bool VEC, int KG>
 __device__ void sinkhorn_run(const SkParams& p, unsigned char* smem_raw) {
   using pot_t = typename Tr<P>::pot_t;
+  using sum_t = typename Tr<P>::sum_t;
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nblk = gridDim.x, b = blockIdx.x;
@@ -186,7 +93,7 @@ __device__ void sinkhorn_run(const SkParams& p, unsigned char* smem_raw) {
   pot_t* u_work = reinterpret_cast<pot_t*>(p.u_work);
   pot_t* v_work[2] = {reinterpret_cast<pot_t*>(p.v_work[0]), reinterpret_cast<pot_t*>(p.v_work[1])};
   pot_t* part_m = reinterpret_cast<pot_t*>(p.part_m);
-  float* part_s = p.part_s;
+  sum_t* part_s = reinterpret_cast<sum_t*>(p.part_s);
 
   // element transform and the log-marginals in this mode's units
   Xf<P> xf;
@@ -217,11 +124,11 @@ __device__ void sinkhorn_run(const SkParams& p, unsigned char* smem_raw) {
     const pot_t* vsrc = p.v_in_smem ? v_s : v_cur;
     for (int panel = 0; panel < npanel; ++panel) {
       pot_t cm[KG][4];
-      float cs[KG][4];
+      sum_t cs[KG][4];
 #pragma unroll
       for (int k = 0; k < KG; ++k)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { cm[k][c] = Tr<P>::init(); cs[k][c] = 0.f; }
+        for (int c = 0; c < 4; ++c) { cm[k][c] = Tr<P>::init(); cs[k][c] = 0; }
       const int gpan = panel * (kPanelCols / 4);
 
       for (int r0 = r_begin; r0 < r_end; r0 += kSkChunk) {
@@ -274,7 +181,7 @@ __device__ void sinkhorn_run(const SkParams& p, unsigned char* smem_raw) {
                 x[q] = xf(cv, u_chunk[(rb + q) & (kSkChunk - 1)]);
                 bm = vmax(bm, x[q]);
               }
-              float acc = cs[k][cc] * expdiff(cm[k][cc], bm);
+              sum_t acc = cs[k][cc] * expdiff(cm[k][cc], bm);
 #pragma unroll
               for (int q = 0; q < 8; ++q) acc += expdiff(x[q], bm);
               cs[k][cc] = acc;
@@ -290,7 +197,7 @@ __device__ void sinkhorn_run(const SkParams& p, unsigned char* smem_raw) {
           const int g = gpan + tid + kSkThreads * k;
           if (g >= ng) continue;
           pot_t* pm = part_m + (int64_t)b * n1p + g * 4;
-          float* ps = part_s + (int64_t)b * n1p + g * 4;
+          sum_t* ps = part_s + (int64_t)b * n1p + g * 4;
 #pragma unroll
           for (int c = 0; c < 4; ++c) { pm[c] = cm[k][c]; ps[c] = cs[k][c]; }
         }
@@ -309,22 +216,22 @@ __device__ void sinkhorn_run(const SkParams& p, unsigned char* smem_raw) {
       const int j = j0 + (tid >> 3);
       const bool act = j < c_end;
       pot_t m = Tr<P>::init();
-      float s = 0.f;
+      sum_t s = 0;
       if (act) {
         for (int c0 = sub; c0 < nblk; c0 += 8 * 4) {
           pot_t mm[4];
-          float ss[4];
+          sum_t ss[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int c = c0 + q * 8;
             if (c < nblk) {
               mm[q] = __ldcg(part_m + (int64_t)c * n1p + j);
               ss[q] = __ldcg(part_s + (int64_t)c * n1p + j);
-            } else { mm[q] = Tr<P>::init(); ss[q] = 0.f; }
+            } else { mm[q] = Tr<P>::init(); ss[q] = 0; }
           }
           pot_t bm = vmax(vmax(mm[0], mm[1]), vmax(mm[2], mm[3]));
           bm = vmax(bm, m);
-          float acc = s * expdiff(m, bm);
+          sum_t acc = s * expdiff(m, bm);
 #pragma unroll
           for (int q = 0; q < 4; ++q) acc += ss[q] * expdiff(mm[q], bm);
           s = acc; m = bm;
@@ -334,7 +241,7 @@ __device__ void sinkhorn_run(const SkParams& p, unsigned char* smem_raw) {
       pot_t gm = m;
 #pragma unroll
       for (int o = 4; o > 0; o >>= 1) gm = vmax(gm, __shfl_xor_sync(0xffffffffu, gm, o));
-      float gs = s * expdiff(m, gm);
+      sum_t gs = s * expdiff(m, gm);
 #pragma unroll
       for (int o = 4; o > 0; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
       if (act && sub == 0) {
@@ -419,6 +326,7 @@ __global__ void __launch_bounds__(kSkThreads, 1) sinkhorn_kernel(const SkParams 
     const float span = (p.normalize ? 1.f : cmax) / p.reg;
     precise = !(span <= 64.f);
   }
+  if (p.run_if == 2 && !precise) return;  // the fast case was taken by sinkhorn_v2_kernel
   if (precise) sinkhorn_run<true, VEC, KG>(p, sk_smem);
   else sinkhorn_run<false, VEC, KG>(p, sk_smem);
 }
@@ -457,12 +365,13 @@ static SkLayout sk_layout(int n0, int n1, int grid) {
   L.v0 = o; o += align_up(n1p * 8, 256);
   L.v1 = o; o += align_up(n1p * 8, 256);
   L.pm = o; o += align_up((size_t)grid * n1p * 8, 256);
-  L.ps = o; o += align_up((size_t)grid * n1p * 4, 256);
+  L.ps = o; o += align_up((size_t)grid * n1p * 8, 256);
   L.ring = o; o += 256;
   L.total = o;
   return L;
 }
 static int sk_grid_upper() { return sm_count() * 2; }
+int sinkhorn_v2_launch(SkParams& p, cudaStream_t s);  // sinkhorn_v2.cu
 
 }  // namespace cfm
 
@@ -488,7 +397,7 @@ static int sk_launch(SkParams& p, size_t smem, void* workspace, cudaStream_t s) 
   p.v_work[0] = w + L.v0;
   p.v_work[1] = w + L.v1;
   p.part_m = w + L.pm;
-  p.part_s = reinterpret_cast<float*>(w + L.ps);
+  p.part_s = w + L.ps;
   p.err_ring = reinterpret_cast<double*>(w + L.ring);
   void* args[] = {(void*)&p};
   CFM_CUDA_OK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(kSkThreads), args, smem, s));
@@ -521,6 +430,25 @@ extern "C" int cfm_sinkhorn_log_f32(const float* M, int n0, int n1, int64_t ldm,
   p.log_u = log_u; p.log_v = log_v; p.status = status; p.err_out = err;
   p.n1p = (n1 + 3) / 4 * 4;
   p.vec = ((n1 & 3) == 0) && ((ldm & 3) == 0) && ((reinterpret_cast<uintptr_t>(M) & 15) == 0);
+  const SkLayout L = sk_layout(n0, n1, sk_grid_upper());
+  {
+    char* w = reinterpret_cast<char*>(workspace);
+    p.u_work = w + L.u; p.v_work[0] = w + L.v0; p.v_work[1] = w + L.v1;
+    p.part_m = w + L.pm; p.part_s = w + L.ps; p.err_ring = reinterpret_cast<double*>(w + L.ring);
+  }
+  // fast fp32 mode on aligned n1 <= 8192: smem-staged kernel (sinkhorn_v2.cu)
+  if (precise == 2) { precise = 0; p.precise = 0; }  // fast arithmetic, generic kernel (cross-checks)
+  else if (precise != 1) {
+    p.run_if = precise < 0 ? 1 : 0;
+    const int rc = sinkhorn_v2_launch(p, s);
+    if (rc < 0) return rc;
+    if (rc == CFM_OK) {
+      if (precise == 0) return CFM_OK;
+      p.run_if = 2;  // auto: the generic kernel below only runs when float64 potentials are needed
+    } else {
+      p.run_if = 0;
+    }
+  }
   const size_t vbytes = (size_t)p.n1p * 8;
   p.v_in_smem = vbytes <= 160 * 1024;
   const size_t smem = p.v_in_smem ? vbytes : 0;

@@ -1,0 +1,483 @@
+// Sinkhorn V2: smem-staged fused sweep fed by bulk async copies (fast fp32 mode, n1 <= 8192,
+// 16-byte aligned rows).  Same algorithm and outputs as sinkhorn.cu (POT sinkhorn_log, reference
+// call site torchcfm/optimal_transport.py:87); different data movement:
+//
+//   * warp 16 is a PRODUCER: it streams the CTA's row slab, R rows per stage, into an S-stage
+//     shared-memory ring with cp.async.bulk (one contiguous 4*n1-byte copy per row, mbarrier
+//     complete_tx).  It runs ahead of the consumers by S stages -- across the grid barriers too,
+//     so HBM keeps streaming while the column partials are being combined.
+//   * warps 0..15 are CONSUMERS.  Thread t owns the same 4*KG columns in both phases, so v_j and the
+//     running column accumulators live in registers for the whole sweep.  Per stage:
+//       row phase   x = M*c2 + v_j for its columns -> warp max -> sum ex2 -> 16 per-warp partials
+//                   -> one named barrier -> every warp folds the 16 partials -> u_r
+//       column phase  re-reads the same smem rows, x = M*c2 + u_r, accumulates into (cm, cs)
+//                   with a lazily updated reference maximum (rescale only when x > cm + 40)
+//     so each element of M costs one HBM read, two smem reads and two ex2 per iteration.
+//   * FACTORED path (taken on the device when span = max|M/reg|*log2(e) <= 40, the regime where
+//     kernel-space Sinkhorn is finite, e.g. BASELINE config 2): E_ij = ex2(M_ij*c2 - kappa) is
+//     formed ONCE per element into registers; the row phase is s_r += E*V_j with V_j = ex2(v_j - vref)
+//     and the column phase c_j += E*U_r with U_r = ex2(u_r - uref): 4 instructions and ONE ex2 per
+//     element per iteration instead of ~11 and two, and the smem stage is released as soon as it
+//     has been read.  Ranges are safe by construction: LSE is 1-Lipschitz, so the spreads of u and
+//     v are <= span and every product stays within 2^(+-3*span) << 2^127.
+//   * per-CTA column partials -> [cta][n1] workspace -> grid barrier -> sliced combine -> v_new,
+//     marginal error -> grid barrier (identical to sinkhorn.cu).
+#include "sinkhorn_common.cuh"
+
+namespace cfm {
+
+constexpr int kV2Consumers = 512;
+constexpr int kV2Threads = kV2Consumers + 32;
+constexpr int kV2Warps = kV2Consumers / 32;
+
+__device__ __forceinline__ uint32_t v2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void v2_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(v2_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void v2_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(v2_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void v2_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(v2_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void v2_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}\n" ::"r"(v2_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void v2_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(v2_smem_u32(dst)), "l"(src), "r"(bytes), "r"(v2_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void v2_consumer_barrier() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+template <int KG, int R>
+__global__ void __launch_bounds__(kV2Threads, 1) sinkhorn_v2_kernel(const SkParams p, const int S) {
+  extern __shared__ __align__(128) unsigned char v2_smem[];
+  cg::grid_group grid = cg::this_grid();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool producer = warp == kV2Warps;
+  const int nblk = gridDim.x, b = blockIdx.x;
+  const int n0 = p.n0, n1 = p.n1, n1p = p.n1p, ng = n1p / 4;
+
+  // device-side mode selection shared with sinkhorn.cu (exactly one of the two kernels works)
+  if (p.run_if != 0) {
+    const float cmax = p.cost_max ? __ldg(p.cost_max) : 0.f;
+    const bool precise = !((p.normalize ? 1.f : cmax) / p.reg <= 64.f);
+    if (precise) return;  // uniform over the whole grid: nobody reaches a grid barrier
+  }
+
+  const size_t stage_floats = (size_t)R * n1p;
+  float* stages = reinterpret_cast<float*>(v2_smem);
+  float2* rowpart = reinterpret_cast<float2*>(stages + (size_t)S * stage_floats);  // [2][R][16]
+  uint64_t* full = reinterpret_cast<uint64_t*>(rowpart + 2 * R * kV2Warps);
+  uint64_t* empty = full + S;
+  __shared__ double red[kV2Warps];
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { v2_mbar_init(&full[s], 1); v2_mbar_init(&empty[s], kV2Warps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  float* u_work = reinterpret_cast<float*>(p.u_work);
+  float* v_work[2] = {reinterpret_cast<float*>(p.v_work[0]), reinterpret_cast<float*>(p.v_work[1])};
+  float* part_m = reinterpret_cast<float*>(p.part_m);
+  float* part_s = reinterpret_cast<float*>(p.part_s);
+
+  const float cmaxv = p.cost_max ? __ldg(p.cost_max) : 1.f;
+  const float c2 = -kLog2e / (p.reg * (p.normalize ? cmaxv : 1.f));
+  const float loga = -log2f((float)n0), logb = -log2f((float)n1);
+  const float cost_hi = p.normalize ? 1.f : cmaxv;   // largest cost value after normalisation
+  const float kappa = c2 * cost_hi * (p.normalize ? cmaxv : 1.f);  // = min_ij M_ij*c2 bound: E >= 1
+  const bool fact = (p.cost_max != nullptr) && (-kappa <= 40.f);   // span in log2 units
+
+  const int base = n0 / nblk, rem = n0 % nblk;
+  const int r_begin = b * base + min(b, rem);
+  const int nrows = base + (b < rem ? 1 : 0);
+  const int nchunks = (nrows + R - 1) / R;
+
+  long long issued = 0, consumed = 0;  // chunk counters over the whole kernel (ring position)
+  long long sweeps = 0;
+
+  // ---- producer: keep the ring full up to `target` chunks ----
+  auto produce_until = [&](long long target) {
+    if (lane != 0) return;
+    while (issued < target) {
+      const int chunk = (int)(issued % nchunks);
+      const int st = (int)(issued % S);
+      const uint32_t use = (uint32_t)(issued / S);
+      v2_mbar_wait(&empty[st], (use & 1u) ^ 1u);
+      const int r0 = r_begin + chunk * R;
+      const int rv = min(R, r_begin + nrows - r0);
+      v2_mbar_expect_tx(&full[st], (uint32_t)rv * (uint32_t)n1 * 4u);
+      for (int r = 0; r < rv; ++r)
+        v2_bulk_load(stages + (size_t)st * stage_floats + (size_t)r * n1p,
+                     p.M + (int64_t)(r0 + r) * p.ldm, (uint32_t)n1 * 4u, &full[st]);
+      ++issued;
+    }
+  };
+
+  // ---- one fused sweep ----
+  auto sweep = [&](bool do_row, bool do_col, const float* v_cur) {
+    if (producer) {
+      // this sweep's chunks plus up to S chunks of the next sweep (drained at exit if unused)
+      produce_until((sweeps + 1) * nchunks + min(S, nchunks));
+      return;
+    }
+    if (fact) {
+      // ---------------- factored (kernel-space in registers) sweep ----------------
+      const float vref = do_row ? __ldcg(v_cur) : 0.f;
+      float4 V[KG];
+      float cs[KG][4];
+#pragma unroll
+      for (int k = 0; k < KG; ++k) {
+        const int g = tid + kV2Consumers * k;
+        V[k] = make_float4(0.f, 0.f, 0.f, 0.f);  // idle columns: weight 0
+        if (g < ng) {
+          if (do_row) {
+            const float* vp = v_cur + g * 4;
+            V[k] = make_float4(ex2f(__ldcg(vp) - vref), ex2f(__ldcg(vp + 1) - vref),
+                               ex2f(__ldcg(vp + 2) - vref), ex2f(__ldcg(vp + 3) - vref));
+          } else {
+            V[k] = make_float4(1.f, 1.f, 1.f, 1.f);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) cs[k][c] = 0.f;
+      }
+      float uref = 0.f;
+      bool have_uref = !do_row;  // prologue: u = 0 everywhere, U = 1
+      for (int chunk = 0; chunk < nchunks; ++chunk) {
+        const int st = (int)(consumed % S);
+        const uint32_t use = (uint32_t)(consumed / S);
+        const int r0 = r_begin + chunk * R;
+        const int rv = min(R, r_begin + nrows - r0);
+        const float* sbase = stages + (size_t)st * stage_floats;
+        float2* rp = rowpart + (size_t)(chunk & 1) * R * kV2Warps;
+        v2_mbar_wait(&full[st], use & 1u);
+        float4 E[R][KG];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int k = 0; k < KG; ++k) {
+            const int g = tid + kV2Consumers * k;
+            E[r][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < rv && g < ng) {
+              const float4 mv = *reinterpret_cast<const float4*>(sbase + (size_t)r * n1p + g * 4);
+              E[r][k] = make_float4(ex2f(fmaf(mv.x, c2, -kappa)), ex2f(fmaf(mv.y, c2, -kappa)),
+                                    ex2f(fmaf(mv.z, c2, -kappa)), ex2f(fmaf(mv.w, c2, -kappa)));
+            }
+          }
+        __syncwarp();
+        if (lane == 0) v2_mbar_arrive(&empty[st]);  // stage can be refilled: data now lives in registers
+        float U[R];
+        if (do_row) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < KG; ++k) {
+              s = fmaf(E[r][k].x, V[k].x, s); s = fmaf(E[r][k].y, V[k].y, s);
+              s = fmaf(E[r][k].z, V[k].z, s); s = fmaf(E[r][k].w, V[k].w, s);
+            }
+            s = warp_sum(s);
+            if (lane == 0) rp[r * kV2Warps + warp] = make_float2(s, 0.f);
+          }
+          v2_consumer_barrier();
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float pr = lane < kV2Warps ? rp[r * kV2Warps + lane].x : 0.f;
+            const float S_r = warp_sum(pr);
+            const float u2 = loga - (kappa + vref + log2f(S_r));  // lse_r = kappa + vref + log2(S_r)
+            if (!have_uref) { uref = u2; have_uref = true; }       // first row of the slab fixes uref
+            U[r] = r < rv ? ex2f(u2 - uref) : 0.f;  // padding rows: E = 0 and U = 0 (never 0*inf)
+            if (warp == 0 && lane == 0 && r < rv) {
+              u_work[r0 + r] = u2;
+              p.log_u[r0 + r] = (double)u2 * kLn2d;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r) U[r] = 1.f;
+        }
+        if (do_col) {
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int k = 0; k < KG; ++k) {
+              cs[k][0] = fmaf(E[r][k].x, U[r], cs[k][0]); cs[k][1] = fmaf(E[r][k].y, U[r], cs[k][1]);
+              cs[k][2] = fmaf(E[r][k].z, U[r], cs[k][2]); cs[k][3] = fmaf(E[r][k].w, U[r], cs[k][3]);
+            }
+        }
+        ++consumed;
+      }
+      if (do_col) {
+        // sum_i ex2(M c2 + u_i) over this slab = cs * 2^(kappa + uref): partial (max, sum) form
+        const float pm = kappa + uref;
+#pragma unroll
+        for (int k = 0; k < KG; ++k) {
+          const int g = tid + kV2Consumers * k;
+          if (g < ng) {
+            *reinterpret_cast<float4*>(part_m + (int64_t)b * n1p + g * 4) = make_float4(pm, pm, pm, pm);
+            *reinterpret_cast<float4*>(part_s + (int64_t)b * n1p + g * 4) =
+                make_float4(cs[k][0], cs[k][1], cs[k][2], cs[k][3]);
+          }
+        }
+      }
+      return;
+    }
+    float4 vreg[KG];
+    float cm[KG][4], cs[KG][4];
+#pragma unroll
+    for (int k = 0; k < KG; ++k) {
+      const int g = tid + kV2Consumers * k;
+      vreg[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (do_row && g < ng) {
+        const float* vp = v_cur + g * 4;  // written by other CTAs before the last grid barrier
+        vreg[k] = make_float4(__ldcg(vp), __ldcg(vp + 1), __ldcg(vp + 2), __ldcg(vp + 3));
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { cm[k][c] = -1.0e30f; cs[k][c] = 0.f; }
+    }
+    const float inf = __int_as_float(0x7f800000);
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+      const int st = (int)(consumed % S);
+      const uint32_t use = (uint32_t)(consumed / S);
+      const int r0 = r_begin + chunk * R;
+      const int rv = min(R, r_begin + nrows - r0);
+      const float* sbase = stages + (size_t)st * stage_floats;
+      float2* rp = rowpart + (size_t)(chunk & 1) * R * kV2Warps;
+      v2_mbar_wait(&full[st], use & 1u);
+      float u2[R];
+      if (do_row) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          float x[KG][4];
+          float tmax = -1.0e30f;
+#pragma unroll
+          for (int k = 0; k < KG; ++k) {
+            const int g = tid + kV2Consumers * k;
+            float4 mv = make_float4(inf, inf, inf, inf);
+            if (r < rv && g < ng) mv = *reinterpret_cast<const float4*>(sbase + (size_t)r * n1p + g * 4);
+            x[k][0] = fmaf(mv.x, c2, vreg[k].x); x[k][1] = fmaf(mv.y, c2, vreg[k].y);
+            x[k][2] = fmaf(mv.z, c2, vreg[k].z); x[k][3] = fmaf(mv.w, c2, vreg[k].w);
+            tmax = fmaxf(tmax, fmaxf(fmaxf(x[k][0], x[k][1]), fmaxf(x[k][2], x[k][3])));
+          }
+          const float wm = warp_max(tmax);
+          float s = 0.f;
+#pragma unroll
+          for (int k = 0; k < KG; ++k)
+            s += (ex2f(x[k][0] - wm) + ex2f(x[k][1] - wm)) + (ex2f(x[k][2] - wm) + ex2f(x[k][3] - wm));
+          s = warp_sum(s);
+          if (lane == 0) rp[r * kV2Warps + warp] = make_float2(wm, s);
+        }
+        v2_consumer_barrier();
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float2 pr = lane < kV2Warps ? rp[r * kV2Warps + lane] : make_float2(-1.0e30f, 0.f);
+          const float gm = warp_max(pr.x);
+          const float gs = warp_sum(pr.y * ex2f(pr.x - gm));
+          u2[r] = loga - (gm + log2f(gs));
+          if (warp == 0 && lane == 0 && r < rv) {
+            u_work[r0 + r] = u2[r];
+            p.log_u[r0 + r] = (double)u2[r] * kLn2d;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) u2[r] = 0.f;
+      }
+      if (do_col) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (r < rv) {
+#pragma unroll
+            for (int k = 0; k < KG; ++k) {
+              const int g = tid + kV2Consumers * k;
+              if (g < ng) {
+                const float4 mv = *reinterpret_cast<const float4*>(sbase + (size_t)r * n1p + g * 4);
+                const float xv[4] = {fmaf(mv.x, c2, u2[r]), fmaf(mv.y, c2, u2[r]), fmaf(mv.z, c2, u2[r]),
+                                     fmaf(mv.w, c2, u2[r])};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  if (xv[c] > cm[k][c] + 40.f) {  // rare: reference maximum lags by more than 2^40
+                    cs[k][c] *= ex2f(cm[k][c] - xv[c]);
+                    cm[k][c] = xv[c];
+                  }
+                  cs[k][c] += ex2f(xv[c] - cm[k][c]);
+                }
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) v2_mbar_arrive(&empty[st]);  // this warp is done reading the stage
+      ++consumed;
+    }
+    if (do_col) {
+#pragma unroll
+      for (int k = 0; k < KG; ++k) {
+        const int g = tid + kV2Consumers * k;
+        if (g < ng) {
+          *reinterpret_cast<float4*>(part_m + (int64_t)b * n1p + g * 4) =
+              make_float4(cm[k][0], cm[k][1], cm[k][2], cm[k][3]);
+          *reinterpret_cast<float4*>(part_s + (int64_t)b * n1p + g * 4) =
+              make_float4(cs[k][0], cs[k][1], cs[k][2], cs[k][3]);
+        }
+      }
+    }
+  };
+
+  // ---- combine a slice of columns over all CTAs' partials (all 544 threads enter) ----
+  auto combine = [&](const float* v_cur, float* v_new, bool have_cur, double* err_slot) {
+    double err_local = 0.0;
+    if (!producer) {
+      const int cpc = (n1 + nblk - 1) / nblk;
+      const int c_begin = b * cpc, c_end = min(n1, c_begin + cpc);
+      const int sub = tid & 7;
+      for (int j0 = c_begin; j0 < c_end; j0 += (kV2Consumers >> 3)) {
+        const int j = j0 + (tid >> 3);
+        const bool act = j < c_end;
+        float m = -1.0e30f, s = 0.f;
+        if (act) {
+          for (int c0 = sub; c0 < nblk; c0 += 32) {
+            float mm[4], ss[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int c = c0 + q * 8;
+              if (c < nblk) {
+                mm[q] = __ldcg(part_m + (int64_t)c * n1p + j);
+                ss[q] = __ldcg(part_s + (int64_t)c * n1p + j);
+              } else { mm[q] = -1.0e30f; ss[q] = 0.f; }
+            }
+            const float bm = fmaxf(fmaxf(fmaxf(mm[0], mm[1]), fmaxf(mm[2], mm[3])), m);
+            float acc = s * ex2f(m - bm);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc += ss[q] * ex2f(mm[q] - bm);
+            s = acc; m = bm;
+          }
+        }
+        float gm = m;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+        float gs = s * ex2f(m - gm);
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
+        if (act && sub == 0) {
+          const float vn = logb - (gm + log2f(gs));
+          v_new[j] = vn;
+          if (have_cur) {
+            const double d = ((double)__ldcg(v_cur + j) - (double)vn) * kLn2d;
+            const double e = expm1(d) / (double)n1;
+            err_local += e * e;
+          }
+        }
+      }
+    }
+    if (err_slot != nullptr) {
+      err_local = warp_sum(err_local);
+      if (!producer && lane == 0) red[warp] = err_local;
+      __syncthreads();
+      if (warp == 0) {
+        double t = lane < kV2Warps ? red[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) atomicAdd(err_slot, t);
+      }
+      __syncthreads();
+    }
+  };
+
+  // ---- prologue: v^0 from u = 0 ----
+  if (b == 0 && tid < 4) p.err_ring[tid] = 0.0;
+  sweep(false, true, nullptr);
+  ++sweeps;
+  grid.sync();
+  combine(nullptr, v_work[0], false, nullptr);
+  grid.sync();
+
+  int cur = 0, iters = 0;
+  bool converged = false;
+  double err = 1.0, prev_check_err = -1.0;
+  for (int it = 0; it < p.max_iters; ++it) {
+    const bool last = (it == p.max_iters - 1);
+    const bool check = (it % p.check_every) == 0;
+    const bool do_col = !last || check;
+    sweep(true, do_col, v_work[cur]);
+    ++sweeps;
+    iters = it + 1;
+    if (!do_col) break;
+    grid.sync();
+    if (b == 0 && tid == 0) p.err_ring[(it + 2) & 3] = 0.0;
+    combine(v_work[cur], v_work[cur ^ 1], true, &p.err_ring[it & 3]);
+    grid.sync();
+    if (check) {
+      err = sqrt(__ldcg(&p.err_ring[it & 3]));
+      if (err < p.stop_thr) { converged = true; break; }
+      if (p.stall_tol > 0.0 && prev_check_err >= 0.0 && err > (1.0 - p.stall_tol) * prev_check_err &&
+          err * sqrt((double)n1) < 1e-5) { converged = true; break; }
+      prev_check_err = err;
+    }
+    if (last) break;
+    cur ^= 1;
+  }
+
+  // ---- drain speculative prefetches so no bulk copy is in flight when the CTA exits ----
+  if (producer && lane == 0) {
+    const long long used = sweeps * nchunks;
+    for (long long c = used; c < issued; ++c) v2_mbar_wait(&full[(int)(c % S)], (uint32_t)(c / S) & 1u);
+  }
+
+  for (int j = b * kV2Threads + tid; j < n1; j += nblk * kV2Threads)
+    p.log_v[j] = (double)__ldcg(v_work[cur] + j) * kLn2d;
+  if (b == 0 && tid == 0) {
+    int flags = 0;
+    if (!converged) flags |= CFM_FLAG_NOT_CONVERGED;
+    if (!(err == err)) flags |= CFM_FLAG_NONFINITE;
+    p.status[0] = flags;
+    p.status[1] = iters;
+    p.status[2] = 0;
+    p.status[3] = fact ? 3 : 2;  // kernel variant: 3 = factored sweep, 2 = log-domain sweep
+    *p.err_out = err;
+  }
+}
+
+template <int KG, int R>
+static int v2_launch_t(SkParams& p, cudaStream_t s) {
+  auto kern = sinkhorn_v2_kernel<KG, R>;
+  const size_t stage_bytes = (size_t)R * p.n1p * 4;
+  const size_t fixed = (size_t)2 * R * kV2Warps * sizeof(float2) + 2 * 8 * sizeof(uint64_t) + 128;
+  int S = (int)((220 * 1024 - fixed) / stage_bytes);
+  if (S > 8) S = 8;
+  if (S < 2) return 1;  // caller falls back to the generic kernel
+  const size_t smem = (size_t)S * stage_bytes + fixed;
+  CFM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CFM_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kV2Threads, smem));
+  if (per_sm < 1) return 1;
+  int grid = sm_count();
+  if (grid > p.n0) grid = p.n0;
+  void* args[] = {(void*)&p, (void*)&S};
+  CFM_CUDA_OK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(kV2Threads), args, smem, s));
+  note_launches(1);
+  return CFM_OK;
+}
+
+// returns CFM_OK when launched, 1 when this shape is not covered (caller uses sinkhorn.cu), <0 on error
+int sinkhorn_v2_launch(SkParams& p, cudaStream_t s) {
+  if (!p.vec || p.n1p > 8192 || p.n1p != p.n1) return 1;
+  const int ng = p.n1p / 4;
+  const int kg = (ng + kV2Consumers - 1) / kV2Consumers;
+  if (kg <= 1) return v2_launch_t<1, 8>(p, s);
+  if (kg <= 2) return v2_launch_t<2, 4>(p, s);
+  return v2_launch_t<4, 2>(p, s);
+}
+
+}  // namespace cfm

@@ -121,7 +121,7 @@ class OTPlanSampler:
         self.warn = warn
         self.num_iter_max = int(num_iter_max)
         self.stop_thr = float(stop_thr)
-        if precision not in ("auto", "fp32", "fp64"):
+        if precision not in ("auto", "fp32", "fp64", "fp32-generic"):
             raise ValueError(f"Unknown precision: {precision}")
         self.precision = precision
         self.stall_tol = float(stall_tol)
@@ -145,9 +145,12 @@ class OTPlanSampler:
         ld = (n1 + 3) // 4 * 4  # 16-byte aligned rows for the float4 / TMA paths
         Mbuf = torch.empty((n0, ld), dtype=torch.float32, device=device)
         cmax = torch.empty(1, dtype=torch.float32, device=device)
-        ws = _ffi.workspace(L.cfm_sqdist_workspace_bytes(n0, n1, d, self.cost_algo), device)
+        # exact OT needs fp32-FMA-grade costs (sigma must not flip): SIMT path unless overridden;
+        # the tcgen05 3xTF32 path (~1e-6 relative, truncating accumulator) serves Sinkhorn
+        algo = self.cost_algo if self.cost_algo else (1 if self.method == "exact" else 0)
+        ws = _ffi.workspace(L.cfm_sqdist_workspace_bytes(n0, n1, d, algo), device)
         _ffi.check(L.cfm_sqdist_f32(_ffi.ptr(a), _ffi.ptr(b), _ffi.ptr(Mbuf), n0, n1, d, ld,
-                                    1 if squared else 0, _ffi.ptr(cmax), self.cost_algo,
+                                    1 if squared else 0, _ffi.ptr(cmax), algo,
                                     _ffi.ptr(ws), ws.numel(), _ffi.stream_ptr(device)),
                    "cfm_sqdist_f32")
         self._last_inputs = (a, b)
@@ -165,11 +168,12 @@ class OTPlanSampler:
         cp.status = torch.zeros(4, dtype=torch.int32, device=dev)
         cp.err = torch.zeros(1, dtype=torch.float64, device=dev)
         ws = _ffi.workspace(L.cfm_sinkhorn_workspace_bytes(n0, n1), dev)
-        prec = {"auto": -1, "fp32": 0, "fp64": 1}[self.precision]
+        prec = {"auto": -1, "fp32": 0, "fp64": 1, "fp32-generic": 2}[self.precision]
         _ffi.check(L.cfm_sinkhorn_log_f32(
             _ffi.ptr(Mbuf), n0, n1, Mbuf.stride(0), float(reg), _ffi.ptr(cmax), int(bool(normalize)),
             int(self.num_iter_max if num_iter_max is None else num_iter_max),
-            float(self.stop_thr if stop_thr is None else stop_thr), 10, prec, self.stall_tol,
+            float(self.stop_thr if stop_thr is None else stop_thr), 10, prec,
+            0.0 if (self.stop_thr if stop_thr is None else stop_thr) <= 0 else self.stall_tol,
             _ffi.ptr(cp.log_u), _ffi.ptr(cp.log_v), _ffi.ptr(cp.status), _ffi.ptr(cp.err),
             _ffi.ptr(ws), ws.numel(), _ffi.stream_ptr(dev)), "cfm_sinkhorn_log_f32")
         return cp

@@ -67,7 +67,7 @@ int cfm_sqdist_f32(const float* x0, const float* x1, float* M, int n0, int n1, i
  * iterations (POT: 10) the column-marginal L2 error is tested against stop_thr.
  * precise: 0 = fp32 exponent arithmetic (|M/reg| <~ 64), 1 = float64 potentials and
  * IEEE fp32 division for -M/reg exactly as NumPy forms it, -1 = choose on device from
- * *cost_max / reg.
+ * *cost_max / reg, 2 = fp32 arithmetic forced onto the generic (L2-reuse) kernel.
  * Outputs: log_u (n0), log_v (n1) float64 natural-log potentials with
  *   plan_ij = exp(-M_ij/reg + log_u_i + log_v_j);
  * stall_tol: 0 = POT's stopping rule only.  > 0 additionally stops at a check when the
