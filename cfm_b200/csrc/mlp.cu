@@ -12,44 +12,9 @@
 // algo 1 (this file): four SIMT fp32 GEMMs with fused bias + activation epilogues (true fp32
 // FMA, the numerics of the reference's cuBLAS sgemm with TF32 off).
 #include "gemm_simt.cuh"
+#include "mlp_common.cuh"
 
 namespace cfm {
-
-struct MlpBlobHeader {
-  int32_t magic, dim, w, out_dim, time_varying, dimp;  // dimp = dim rounded up to 4
-  int64_t off_w0x, off_w0t, off_b0, off_w1, off_b1, off_w2, off_b2, off_w3, off_b3, off_tc, total;
-};
-constexpr int32_t kMlpMagic = 0x4d4c5031;  // "MLP1"
-
-size_t mlp_tc_blob_bytes(int dim, int w, int out_dim);  // mlp_tc.cu
-int mlp_tc_prepare(const MlpBlobHeader& h, void* blob, cudaStream_t s);
-int mlp_tc_supported(int batch, int dim, int w, int out_dim);
-size_t mlp_tc_workspace_bytes(int batch, int dim, int w, int out_dim);
-int mlp_tc_forward(const MlpBlobHeader& h, const void* blob, const float* x, int batch,
-                   const float* t_dev, float t_host, int act, float* y, void* ws, size_t ws_bytes,
-                   cudaStream_t s);
-
-static MlpBlobHeader mlp_layout(int dim, int w, int out_dim, int tv) {
-  MlpBlobHeader h;
-  memset(&h, 0, sizeof(h));
-  h.magic = kMlpMagic; h.dim = dim; h.w = w; h.out_dim = out_dim; h.time_varying = tv;
-  h.dimp = (dim + 3) / 4 * 4;
-  size_t o = align_up(sizeof(MlpBlobHeader), 256);
-  auto take = [&](size_t floats) { size_t r = o; o += align_up(floats * 4, 256); return (int64_t)r; };
-  h.off_w0x = take((size_t)w * h.dimp);
-  h.off_w0t = take(w);
-  h.off_b0 = take(w);
-  h.off_w1 = take((size_t)w * w);
-  h.off_b1 = take(w);
-  h.off_w2 = take((size_t)w * w);
-  h.off_b2 = take(w);
-  h.off_w3 = take((size_t)out_dim * w);
-  h.off_b3 = take(out_dim);
-  h.off_tc = (int64_t)o;
-  o += mlp_tc_blob_bytes(dim, w, out_dim);
-  h.total = (int64_t)o;
-  return h;
-}
 
 __global__ void mlp_split_w0_kernel(const float* __restrict__ W0, int w, int dim, int in0, int dimp,
                                     float* __restrict__ w0x, float* __restrict__ w0t) {
@@ -57,15 +22,6 @@ __global__ void mlp_split_w0_kernel(const float* __restrict__ W0, int w, int dim
   for (int k = threadIdx.x; k < dimp; k += blockDim.x)
     w0x[(int64_t)n * dimp + k] = k < dim ? W0[(int64_t)n * in0 + k] : 0.f;
   if (threadIdx.x == 0) w0t[n] = in0 > dim ? W0[(int64_t)n * in0 + dim] : 0.f;
-}
-
-__device__ __forceinline__ float act_apply(float x, int act) {
-  if (act == CFM_ACT_SELU) {
-    const float scale = 1.0507009873554804934193349852946f;
-    const float negcoef = (float)(1.6732632423543772848170429916717 * 1.0507009873554804934193349852946);
-    return x > 0.f ? x * scale : expm1f(x) * negcoef;
-  }
-  return x / (1.f + __expf(-x));  // SiLU
 }
 
 struct BiasActEpilogue {

@@ -159,6 +159,111 @@ __global__ void draw_kernel(E ent, int n0, int n1, const double* __restrict__ ro
   }
 }
 
+
+// ---- fast draw for Sinkhorn potentials whose last update was the row update ---------------------
+// Row masses are then exactly a_i = 1/n0 by construction (u_i = log a_i - LSE_j(...)), so the row is
+// i = floor(u * n0) and only the within-row inversion needs the plan: weights w_j = ex2(M_ij*c2 + v2_j)
+// (the u_i factor cancels in the row-normalised cdf).  One warp per draw, two coalesced float4 passes
+// over the row (the second one hits L1/L2): pass A totals the row, pass B walks 1024-column blocks
+// to the one holding the target and resolves it with a warp scan.
+__global__ void draw_uniform_rows_kernel(const float* __restrict__ M, int n0, int n1, int64_t ldm,
+                                         float reg, const float* __restrict__ cost_max, int normalize,
+                                         const double* __restrict__ lv, const double* __restrict__ uniforms,
+                                         int n_draws, int64_t* __restrict__ i_out,
+                                         int64_t* __restrict__ j_out, int32_t* status) {
+  const int draw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (draw >= n_draws) return;
+  const double u = uniforms[draw];
+  int i = (int)(u * (double)n0);
+  if (i >= n0) i = n0 - 1;
+  const double frac = u * (double)n0 - (double)i;  // position inside row i's cdf cell, in [0, 1)
+  const float scale = normalize ? __ldg(cost_max) : 1.f;
+  const float c2 = -kLog2e / (reg * scale);
+  const float* row = M + (int64_t)i * ldm;
+  const bool vec = ((ldm & 3) == 0) && ((n1 & 3) == 0) && ((reinterpret_cast<uintptr_t>(M) & 15) == 0);
+  const float vref = (float)(lv[0] * kLog2ed);
+  auto weight = [&](int j) -> float {
+    return ex2f(fmaf(__ldg(row + j), c2, (float)(lv[j] * kLog2ed) - vref));
+  };
+  auto weight4 = [&](int j) -> float4 {
+    const float4 m = *reinterpret_cast<const float4*>(row + j);
+    return make_float4(ex2f(fmaf(m.x, c2, (float)(lv[j] * kLog2ed) - vref)),
+                       ex2f(fmaf(m.y, c2, (float)(lv[j + 1] * kLog2ed) - vref)),
+                       ex2f(fmaf(m.z, c2, (float)(lv[j + 2] * kLog2ed) - vref)),
+                       ex2f(fmaf(m.w, c2, (float)(lv[j + 3] * kLog2ed) - vref)));
+  };
+  // pass A: row total
+  float part = 0.f;
+  if (vec) {
+    for (int j = lane * 4; j < n1; j += 128) { const float4 w = weight4(j); part += (w.x + w.y) + (w.z + w.w); }
+  } else {
+    for (int j = lane; j < n1; j += 32) part += weight(j);
+  }
+  const double total = warp_sum((double)part);
+  int jsel = -1;
+  if (!(total > 0.0) || !isfinite(total)) {
+    if (lane == 0 && status) atomicOr(status, CFM_FLAG_NONFINITE);
+    jsel = min(n1 - 1, (int)(frac * (double)n1));
+  } else {
+    const double target = frac * total;
+    double run = 0.0;
+    // pass B: coarse blocks of 1024 columns, then a fine scan inside the block that crosses
+    for (int b0 = 0; b0 < n1 && jsel < 0; b0 += 1024) {
+      const int bend = min(n1, b0 + 1024);
+      float bp = 0.f;
+      if (vec) {
+        for (int j = b0 + lane * 4; j < bend; j += 128) { const float4 w = weight4(j); bp += (w.x + w.y) + (w.z + w.w); }
+      } else {
+        for (int j = b0 + lane; j < bend; j += 32) bp += weight(j);
+      }
+      const double bsum = warp_sum((double)bp);
+      if (run + bsum > target || bend == n1) {
+        // fine scan: 128 (vec) or 32 (scalar) columns per step, in natural column order
+        const int step = vec ? 128 : 32;
+        for (int j0 = b0; j0 < bend && jsel < 0; j0 += step) {
+          float w[4] = {0.f, 0.f, 0.f, 0.f};
+          const int j = j0 + (vec ? lane * 4 : lane);
+          if (j < bend) {
+            if (vec) { const float4 q = weight4(j); w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w; }
+            else w[0] = weight(j);
+          }
+          const double mine = (double)((w[0] + w[1]) + (w[2] + w[3]));
+          double incl = mine;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+          }
+          const bool hit = (j < bend) && (run + incl > target);
+          const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+          if (ballot) {
+            const int src = __ffs(ballot) - 1;
+            // the winning lane resolves the element inside its float4
+            int jj = -1;
+            if (lane == src) {
+              double r2 = run + incl - mine;
+              const int cnt = vec ? 4 : 1;
+              jj = j + cnt - 1;
+              for (int c = 0; c < cnt; ++c) { r2 += (double)w[c]; if (r2 > target) { jj = j + c; break; } }
+            }
+            jsel = __shfl_sync(0xffffffffu, jj, src);
+          }
+          run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (jsel < 0) jsel = bend - 1;  // rounding at the very end of the row
+      } else {
+        run += bsum;
+      }
+    }
+    if (jsel < 0) jsel = n1 - 1;
+  }
+  if (lane == 0) {
+    i_out[draw] = i;
+    j_out[draw] = jsel;
+  }
+}
+
 __global__ void perm_draw_kernel(const int32_t* __restrict__ sigma, const double* __restrict__ stairs,
                                  int n, const double* __restrict__ uniforms, int n_draws,
                                  int64_t* __restrict__ i_out, int64_t* __restrict__ j_out) {
@@ -196,13 +301,20 @@ extern "C" size_t cfm_plan_sample_workspace_bytes(int n0) { return ((size_t)2 * 
 
 extern "C" int cfm_plan_sample(const float* M, int n0, int n1, int64_t ldm, float reg,
                                const float* cost_max, int normalize, const double* log_u,
-                               const double* log_v, const double* uniforms, int n_draws,
-                               int64_t* i_out, int64_t* j_out, int32_t* status, void* workspace,
-                               size_t workspace_bytes, void* stream) {
+                               const double* log_v, int uniform_rows, const double* uniforms,
+                               int n_draws, int64_t* i_out, int64_t* j_out, int32_t* status,
+                               void* workspace, size_t workspace_bytes, void* stream) {
   CFM_REQUIRE(M && log_u && log_v && (n_draws == 0 || (uniforms && i_out && j_out)),
               "cfm_plan_sample: null pointer");
   CFM_REQUIRE(n0 > 0 && n1 > 0 && ldm >= n1 && n_draws >= 0, "cfm_plan_sample: bad shape");
   CFM_REQUIRE(!(normalize && !cost_max), "cfm_plan_sample: normalize needs cost_max");
+  if (uniform_rows) {
+    if (n_draws == 0) return CFM_OK;
+    draw_uniform_rows_kernel<<<(n_draws + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+        M, n0, n1, ldm, reg, cost_max, normalize, log_v, uniforms, n_draws, i_out, j_out, status); ::cfm::note_launches(1);
+    CFM_CUDA_OK(cudaGetLastError());
+    return CFM_OK;
+  }
   PotEntry ent{M, ldm, reg, cost_max, normalize, log_u, log_v};
   return sample_common(ent, n0, n1, uniforms, n_draws, i_out, j_out, status, workspace,
                        workspace_bytes, (cudaStream_t)stream);

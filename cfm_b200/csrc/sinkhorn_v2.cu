@@ -2,11 +2,12 @@
 // 16-byte aligned rows).  Same algorithm and outputs as sinkhorn.cu (POT sinkhorn_log, reference
 // call site torchcfm/optimal_transport.py:87); different data movement:
 //
-//   * warp 16 is a PRODUCER: it streams the CTA's row slab, R rows per stage, into an S-stage
-//     shared-memory ring with cp.async.bulk (one contiguous 4*n1-byte copy per row, mbarrier
-//     complete_tx).  It runs ahead of the consumers by S stages -- across the grid barriers too,
-//     so HBM keeps streaming while the column partials are being combined.
-//   * warps 0..15 are CONSUMERS.  Thread t owns the same 4*KG columns in both phases, so v_j and the
+//   * the CTA's row slab is streamed, R rows per stage, into an S-stage shared-memory ring with
+//     cp.async.bulk (one contiguous 4*n1-byte copy per row, mbarrier complete_tx).  Thread 0 issues
+//     the refill of a stage right after the per-chunk block barrier that proves every warp has
+//     finished reading it, so the ring stays S chunks ahead -- across the grid barriers too (the
+//     copies for the next sweep are already in flight while the column partials are combined).
+//   * all 16 warps are consumers.  Thread t owns the same 4*KG columns in both phases, so v_j and the
 //     running column accumulators live in registers for the whole sweep.  Per stage:
 //       row phase   x = M*c2 + v_j for its columns -> warp max -> sum ex2 -> 16 per-warp partials
 //                   -> one named barrier -> every warp folds the 16 partials -> u_r
@@ -27,7 +28,7 @@
 namespace cfm {
 
 constexpr int kV2Consumers = 512;
-constexpr int kV2Threads = kV2Consumers + 32;
+constexpr int kV2Threads = kV2Consumers;  // no dedicated producer warp: thread 0 refills after each barrier
 constexpr int kV2Warps = kV2Consumers / 32;
 
 __device__ __forceinline__ uint32_t v2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -62,7 +63,6 @@ __global__ void __launch_bounds__(kV2Threads, 1) sinkhorn_v2_kernel(const SkPara
   extern __shared__ __align__(128) unsigned char v2_smem[];
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool producer = warp == kV2Warps;
   const int nblk = gridDim.x, b = blockIdx.x;
   const int n0 = p.n0, n1 = p.n1, n1p = p.n1p, ng = n1p / 4;
 
@@ -73,15 +73,14 @@ __global__ void __launch_bounds__(kV2Threads, 1) sinkhorn_v2_kernel(const SkPara
     if (precise) return;  // uniform over the whole grid: nobody reaches a grid barrier
   }
 
-  const size_t stage_floats = (size_t)R * n1p;
+  const uint32_t stage_floats = (uint32_t)R * (uint32_t)n1p;
   float* stages = reinterpret_cast<float*>(v2_smem);
   float2* rowpart = reinterpret_cast<float2*>(stages + (size_t)S * stage_floats);  // [2][R][16]
   uint64_t* full = reinterpret_cast<uint64_t*>(rowpart + 2 * R * kV2Warps);
-  uint64_t* empty = full + S;
   __shared__ double red[kV2Warps];
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { v2_mbar_init(&full[s], 1); v2_mbar_init(&empty[s], kV2Warps); }
+    for (int s = 0; s < S; ++s) v2_mbar_init(&full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -94,55 +93,54 @@ __global__ void __launch_bounds__(kV2Threads, 1) sinkhorn_v2_kernel(const SkPara
   const float cmaxv = p.cost_max ? __ldg(p.cost_max) : 1.f;
   const float c2 = -kLog2e / (p.reg * (p.normalize ? cmaxv : 1.f));
   const float loga = -log2f((float)n0), logb = -log2f((float)n1);
-  const float cost_hi = p.normalize ? 1.f : cmaxv;   // largest cost value after normalisation
-  const float kappa = c2 * cost_hi * (p.normalize ? cmaxv : 1.f);  // = min_ij M_ij*c2 bound: E >= 1
-  const bool fact = (p.cost_max != nullptr) && (-kappa <= 40.f);   // span in log2 units
+  const float kappa = c2 * cmaxv;  // = min_ij M_ij*c2 (most negative exponent), so E = ex2(M*c2 - kappa) >= 1
+  const bool fact = (p.cost_max != nullptr) && (-kappa <= 40.f);  // span in log2 units
 
   const int base = n0 / nblk, rem = n0 % nblk;
   const int r_begin = b * base + min(b, rem);
   const int nrows = base + (b < rem ? 1 : 0);
   const int nchunks = (nrows + R - 1) / R;
 
-  long long issued = 0, consumed = 0;  // chunk counters over the whole kernel (ring position)
-  long long sweeps = 0;
+  // ---- ring bookkeeping (incremental: no 64-bit div/mod in the hot loop) ----
+  // chunk sequence q = 0,1,2,... over ALL sweeps; chunk q sits in stage q % S, slab chunk q % nchunks
+  int c_st = 0;             // consumers: stage of the next chunk to consume
+  uint32_t c_par = 0;       //            parity to wait for on full[c_st]
+  int p_st = 0, p_chunk = 0;  // producer (thread 0): stage / slab chunk of the next chunk to issue
+  long long issued = 0, consumed_total = 0;
+  bool gvalid[KG];
+#pragma unroll
+  for (int k = 0; k < KG; ++k) gvalid[k] = (tid + kV2Consumers * k) < ng;
+  const int tcol = tid * 4;  // first owned column; group k adds 2048*k
 
-  // ---- producer: keep the ring full up to `target` chunks ----
-  auto produce_until = [&](long long target) {
-    if (lane != 0) return;
-    while (issued < target) {
-      const int chunk = (int)(issued % nchunks);
-      const int st = (int)(issued % S);
-      const uint32_t use = (uint32_t)(issued / S);
-      v2_mbar_wait(&empty[st], (use & 1u) ^ 1u);
-      const int r0 = r_begin + chunk * R;
-      const int rv = min(R, r_begin + nrows - r0);
-      v2_mbar_expect_tx(&full[st], (uint32_t)rv * (uint32_t)n1 * 4u);
-      for (int r = 0; r < rv; ++r)
-        v2_bulk_load(stages + (size_t)st * stage_floats + (size_t)r * n1p,
-                     p.M + (int64_t)(r0 + r) * p.ldm, (uint32_t)n1 * 4u, &full[st]);
-      ++issued;
-    }
+  // thread 0: issue the bulk copies of the next chunk into its (free) stage
+  auto issue_next = [&]() {
+    const int r0 = r_begin + p_chunk * R;
+    const int rv = min(R, r_begin + nrows - r0);
+    v2_mbar_expect_tx(&full[p_st], (uint32_t)rv * (uint32_t)n1 * 4u);
+    for (int r = 0; r < rv; ++r)
+      v2_bulk_load(stages + (size_t)p_st * stage_floats + (size_t)r * n1p,
+                   p.M + (int64_t)(r0 + r) * p.ldm, (uint32_t)n1 * 4u, &full[p_st]);
+    ++issued;
+    if (++p_chunk == nchunks) p_chunk = 0;
+    if (++p_st == S) p_st = 0;
   };
+  if (tid == 0)
+    for (int q = 0; q < S; ++q) issue_next();  // initial fill (wraps into the next sweep if S > nchunks)
 
   // ---- one fused sweep ----
   auto sweep = [&](bool do_row, bool do_col, const float* v_cur) {
-    if (producer) {
-      // this sweep's chunks plus up to S chunks of the next sweep (drained at exit if unused)
-      produce_until((sweeps + 1) * nchunks + min(S, nchunks));
-      return;
-    }
     if (fact) {
       // ---------------- factored (kernel-space in registers) sweep ----------------
       const float vref = do_row ? __ldcg(v_cur) : 0.f;
+      const float nkap = -kappa;
       float4 V[KG];
       float cs[KG][4];
 #pragma unroll
       for (int k = 0; k < KG; ++k) {
-        const int g = tid + kV2Consumers * k;
         V[k] = make_float4(0.f, 0.f, 0.f, 0.f);  // idle columns: weight 0
-        if (g < ng) {
+        if (gvalid[k]) {
           if (do_row) {
-            const float* vp = v_cur + g * 4;
+            const float* vp = v_cur + tcol + kV2Consumers * 4 * k;
             V[k] = make_float4(ex2f(__ldcg(vp) - vref), ex2f(__ldcg(vp + 1) - vref),
                                ex2f(__ldcg(vp + 2) - vref), ex2f(__ldcg(vp + 3) - vref));
           } else {
@@ -155,29 +153,26 @@ __global__ void __launch_bounds__(kV2Threads, 1) sinkhorn_v2_kernel(const SkPara
       float uref = 0.f;
       bool have_uref = !do_row;  // prologue: u = 0 everywhere, U = 1
       for (int chunk = 0; chunk < nchunks; ++chunk) {
-        const int st = (int)(consumed % S);
-        const uint32_t use = (uint32_t)(consumed / S);
         const int r0 = r_begin + chunk * R;
         const int rv = min(R, r_begin + nrows - r0);
-        const float* sbase = stages + (size_t)st * stage_floats;
-        float2* rp = rowpart + (size_t)(chunk & 1) * R * kV2Warps;
-        v2_mbar_wait(&full[st], use & 1u);
+        const float* sbase = stages + (uint32_t)c_st * stage_floats + tcol;
+        float2* rp = rowpart + (chunk & 1) * R * kV2Warps;
+        v2_mbar_wait(&full[c_st], c_par);
         float4 E[R][KG];
 #pragma unroll
-        for (int r = 0; r < R; ++r)
+        for (int r = 0; r < R; ++r) {
+          const float* srow = sbase + r * n1p;
 #pragma unroll
           for (int k = 0; k < KG; ++k) {
-            const int g = tid + kV2Consumers * k;
             E[r][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < rv && g < ng) {
-              const float4 mv = *reinterpret_cast<const float4*>(sbase + (size_t)r * n1p + g * 4);
-              E[r][k] = make_float4(ex2f(fmaf(mv.x, c2, -kappa)), ex2f(fmaf(mv.y, c2, -kappa)),
-                                    ex2f(fmaf(mv.z, c2, -kappa)), ex2f(fmaf(mv.w, c2, -kappa)));
+            if (gvalid[k] && r < rv) {
+              const float4 mv = *reinterpret_cast<const float4*>(srow + kV2Consumers * 4 * k);
+              E[r][k] = make_float4(ex2f(fmaf(mv.x, c2, nkap)), ex2f(fmaf(mv.y, c2, nkap)),
+                                    ex2f(fmaf(mv.z, c2, nkap)), ex2f(fmaf(mv.w, c2, nkap)));
             }
           }
-        __syncwarp();
-        if (lane == 0) v2_mbar_arrive(&empty[st]);  // stage can be refilled: data now lives in registers
-        float U[R];
+        }
+        if (++c_st == S) { c_st = 0; c_par ^= 1u; }
         if (do_row) {
 #pragma unroll
           for (int r = 0; r < R; ++r) {
@@ -190,7 +185,13 @@ __global__ void __launch_bounds__(kV2Threads, 1) sinkhorn_v2_kernel(const SkPara
             s = warp_sum(s);
             if (lane == 0) rp[r * kV2Warps + warp] = make_float2(s, 0.f);
           }
-          v2_consumer_barrier();
+        }
+        // every warp has now copied its part of the stage into registers: after this barrier the
+        // stage is free, so thread 0 refills it with the chunk S positions ahead
+        v2_consumer_barrier();
+        if (tid == 0) issue_next();
+        float U[R];
+        if (do_row) {
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             const float pr = lane < kV2Warps ? rp[r * kV2Warps + lane].x : 0.f;
@@ -216,31 +217,30 @@ __global__ void __launch_bounds__(kV2Threads, 1) sinkhorn_v2_kernel(const SkPara
               cs[k][2] = fmaf(E[r][k].z, U[r], cs[k][2]); cs[k][3] = fmaf(E[r][k].w, U[r], cs[k][3]);
             }
         }
-        ++consumed;
       }
+      consumed_total += nchunks;
       if (do_col) {
         // sum_i ex2(M c2 + u_i) over this slab = cs * 2^(kappa + uref): partial (max, sum) form
         const float pm = kappa + uref;
 #pragma unroll
-        for (int k = 0; k < KG; ++k) {
-          const int g = tid + kV2Consumers * k;
-          if (g < ng) {
-            *reinterpret_cast<float4*>(part_m + (int64_t)b * n1p + g * 4) = make_float4(pm, pm, pm, pm);
-            *reinterpret_cast<float4*>(part_s + (int64_t)b * n1p + g * 4) =
+        for (int k = 0; k < KG; ++k)
+          if (gvalid[k]) {
+            *reinterpret_cast<float4*>(part_m + (int64_t)b * n1p + tcol + kV2Consumers * 4 * k) =
+                make_float4(pm, pm, pm, pm);
+            *reinterpret_cast<float4*>(part_s + (int64_t)b * n1p + tcol + kV2Consumers * 4 * k) =
                 make_float4(cs[k][0], cs[k][1], cs[k][2], cs[k][3]);
           }
-        }
       }
       return;
     }
+    // ---------------- log-domain sweep (span > 40): two smem reads per element ----------------
     float4 vreg[KG];
     float cm[KG][4], cs[KG][4];
 #pragma unroll
     for (int k = 0; k < KG; ++k) {
-      const int g = tid + kV2Consumers * k;
       vreg[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (do_row && g < ng) {
-        const float* vp = v_cur + g * 4;  // written by other CTAs before the last grid barrier
+      if (do_row && gvalid[k]) {
+        const float* vp = v_cur + tcol + kV2Consumers * 4 * k;  // written before the last grid barrier
         vreg[k] = make_float4(__ldcg(vp), __ldcg(vp + 1), __ldcg(vp + 2), __ldcg(vp + 3));
       }
 #pragma unroll
@@ -248,13 +248,12 @@ __global__ void __launch_bounds__(kV2Threads, 1) sinkhorn_v2_kernel(const SkPara
     }
     const float inf = __int_as_float(0x7f800000);
     for (int chunk = 0; chunk < nchunks; ++chunk) {
-      const int st = (int)(consumed % S);
-      const uint32_t use = (uint32_t)(consumed / S);
       const int r0 = r_begin + chunk * R;
       const int rv = min(R, r_begin + nrows - r0);
-      const float* sbase = stages + (size_t)st * stage_floats;
-      float2* rp = rowpart + (size_t)(chunk & 1) * R * kV2Warps;
-      v2_mbar_wait(&full[st], use & 1u);
+      const float* sbase = stages + (uint32_t)c_st * stage_floats + tcol;
+      float2* rp = rowpart + (chunk & 1) * R * kV2Warps;
+      v2_mbar_wait(&full[c_st], c_par);
+      if (++c_st == S) { c_st = 0; c_par ^= 1u; }
       float u2[R];
       if (do_row) {
 #pragma unroll
@@ -263,9 +262,8 @@ __global__ void __launch_bounds__(kV2Threads, 1) sinkhorn_v2_kernel(const SkPara
           float tmax = -1.0e30f;
 #pragma unroll
           for (int k = 0; k < KG; ++k) {
-            const int g = tid + kV2Consumers * k;
             float4 mv = make_float4(inf, inf, inf, inf);
-            if (r < rv && g < ng) mv = *reinterpret_cast<const float4*>(sbase + (size_t)r * n1p + g * 4);
+            if (gvalid[k] && r < rv) mv = *reinterpret_cast<const float4*>(sbase + r * n1p + kV2Consumers * 4 * k);
             x[k][0] = fmaf(mv.x, c2, vreg[k].x); x[k][1] = fmaf(mv.y, c2, vreg[k].y);
             x[k][2] = fmaf(mv.z, c2, vreg[k].z); x[k][3] = fmaf(mv.w, c2, vreg[k].w);
             tmax = fmaxf(tmax, fmaxf(fmaxf(x[k][0], x[k][1]), fmaxf(x[k][2], x[k][3])));
@@ -278,9 +276,12 @@ __global__ void __launch_bounds__(kV2Threads, 1) sinkhorn_v2_kernel(const SkPara
           s = warp_sum(s);
           if (lane == 0) rp[r * kV2Warps + warp] = make_float2(wm, s);
         }
-        v2_consumer_barrier();
+      }
+      v2_consumer_barrier();
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
+      for (int r = 0; r < R; ++r) {
+        u2[r] = 0.f;
+        if (do_row) {
           const float2 pr = lane < kV2Warps ? rp[r * kV2Warps + lane] : make_float2(-1.0e30f, 0.f);
           const float gm = warp_max(pr.x);
           const float gs = warp_sum(pr.y * ex2f(pr.x - gm));
@@ -290,9 +291,6 @@ __global__ void __launch_bounds__(kV2Threads, 1) sinkhorn_v2_kernel(const SkPara
             p.log_u[r0 + r] = (double)u2[r] * kLn2d;
           }
         }
-      } else {
-#pragma unroll
-        for (int r = 0; r < R; ++r) u2[r] = 0.f;
       }
       if (do_col) {
 #pragma unroll
@@ -300,9 +298,8 @@ __global__ void __launch_bounds__(kV2Threads, 1) sinkhorn_v2_kernel(const SkPara
           if (r < rv) {
 #pragma unroll
             for (int k = 0; k < KG; ++k) {
-              const int g = tid + kV2Consumers * k;
-              if (g < ng) {
-                const float4 mv = *reinterpret_cast<const float4*>(sbase + (size_t)r * n1p + g * 4);
+              if (gvalid[k]) {
+                const float4 mv = *reinterpret_cast<const float4*>(sbase + r * n1p + kV2Consumers * 4 * k);
                 const float xv[4] = {fmaf(mv.x, c2, u2[r]), fmaf(mv.y, c2, u2[r]), fmaf(mv.z, c2, u2[r]),
                                      fmaf(mv.w, c2, u2[r])};
 #pragma unroll
@@ -318,73 +315,71 @@ __global__ void __launch_bounds__(kV2Threads, 1) sinkhorn_v2_kernel(const SkPara
           }
         }
       }
-      __syncwarp();
-      if (lane == 0) v2_mbar_arrive(&empty[st]);  // this warp is done reading the stage
-      ++consumed;
+      // the stage is read again by the column phase: it is free only once every warp is past this
+      // point, which the NEXT chunk's barrier (or the one below for the last chunk) certifies
+      v2_consumer_barrier();
+      if (tid == 0) issue_next();
     }
+    consumed_total += nchunks;
     if (do_col) {
 #pragma unroll
-      for (int k = 0; k < KG; ++k) {
-        const int g = tid + kV2Consumers * k;
-        if (g < ng) {
-          *reinterpret_cast<float4*>(part_m + (int64_t)b * n1p + g * 4) =
+      for (int k = 0; k < KG; ++k)
+        if (gvalid[k]) {
+          *reinterpret_cast<float4*>(part_m + (int64_t)b * n1p + tcol + kV2Consumers * 4 * k) =
               make_float4(cm[k][0], cm[k][1], cm[k][2], cm[k][3]);
-          *reinterpret_cast<float4*>(part_s + (int64_t)b * n1p + g * 4) =
+          *reinterpret_cast<float4*>(part_s + (int64_t)b * n1p + tcol + kV2Consumers * 4 * k) =
               make_float4(cs[k][0], cs[k][1], cs[k][2], cs[k][3]);
         }
-      }
     }
   };
 
-  // ---- combine a slice of columns over all CTAs' partials (all 544 threads enter) ----
+  // ---- combine a slice of columns over all CTAs' partials ----
   auto combine = [&](const float* v_cur, float* v_new, bool have_cur, double* err_slot) {
     double err_local = 0.0;
-    if (!producer) {
-      const int cpc = (n1 + nblk - 1) / nblk;
-      const int c_begin = b * cpc, c_end = min(n1, c_begin + cpc);
-      const int sub = tid & 7;
-      for (int j0 = c_begin; j0 < c_end; j0 += (kV2Consumers >> 3)) {
-        const int j = j0 + (tid >> 3);
-        const bool act = j < c_end;
-        float m = -1.0e30f, s = 0.f;
-        if (act) {
-          for (int c0 = sub; c0 < nblk; c0 += 32) {
-            float mm[4], ss[4];
+    const int cpc = (n1 + nblk - 1) / nblk;
+    const int c_begin = b * cpc, c_end = min(n1, c_begin + cpc);
+    const int sub = tid & 7;
+    for (int j0 = c_begin; j0 < c_end; j0 += (kV2Consumers >> 3)) {
+      const int j = j0 + (tid >> 3);
+      const bool act = j < c_end;
+      float m = -1.0e30f, s = 0.f;
+      if (act) {
+        for (int c0 = sub; c0 < nblk; c0 += 32) {
+          float mm[4], ss[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int c = c0 + q * 8;
-              if (c < nblk) {
-                mm[q] = __ldcg(part_m + (int64_t)c * n1p + j);
-                ss[q] = __ldcg(part_s + (int64_t)c * n1p + j);
-              } else { mm[q] = -1.0e30f; ss[q] = 0.f; }
-            }
-            const float bm = fmaxf(fmaxf(fmaxf(mm[0], mm[1]), fmaxf(mm[2], mm[3])), m);
-            float acc = s * ex2f(m - bm);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) acc += ss[q] * ex2f(mm[q] - bm);
-            s = acc; m = bm;
+          for (int q = 0; q < 4; ++q) {
+            const int c = c0 + q * 8;
+            if (c < nblk) {
+              mm[q] = __ldcg(part_m + (int64_t)c * n1p + j);
+              ss[q] = __ldcg(part_s + (int64_t)c * n1p + j);
+            } else { mm[q] = -1.0e30f; ss[q] = 0.f; }
           }
+          const float bm = fmaxf(fmaxf(fmaxf(mm[0], mm[1]), fmaxf(mm[2], mm[3])), m);
+          float acc = s * ex2f(m - bm);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc += ss[q] * ex2f(mm[q] - bm);
+          s = acc; m = bm;
         }
-        float gm = m;
+      }
+      float gm = m;
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
-        float gs = s * ex2f(m - gm);
+      for (int o = 4; o > 0; o >>= 1) gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+      float gs = s * ex2f(m - gm);
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
-        if (act && sub == 0) {
-          const float vn = logb - (gm + log2f(gs));
-          v_new[j] = vn;
-          if (have_cur) {
-            const double d = ((double)__ldcg(v_cur + j) - (double)vn) * kLn2d;
-            const double e = expm1(d) / (double)n1;
-            err_local += e * e;
-          }
+      for (int o = 4; o > 0; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
+      if (act && sub == 0) {
+        const float vn = logb - (gm + log2f(gs));
+        v_new[j] = vn;
+        if (have_cur) {
+          const double d = ((double)__ldcg(v_cur + j) - (double)vn) * kLn2d;
+          const double e = expm1(d) / (double)n1;
+          err_local += e * e;
         }
       }
     }
     if (err_slot != nullptr) {
       err_local = warp_sum(err_local);
-      if (!producer && lane == 0) red[warp] = err_local;
+      if (lane == 0) red[warp] = err_local;
       __syncthreads();
       if (warp == 0) {
         double t = lane < kV2Warps ? red[lane] : 0.0;
@@ -398,7 +393,6 @@ __global__ void __launch_bounds__(kV2Threads, 1) sinkhorn_v2_kernel(const SkPara
   // ---- prologue: v^0 from u = 0 ----
   if (b == 0 && tid < 4) p.err_ring[tid] = 0.0;
   sweep(false, true, nullptr);
-  ++sweeps;
   grid.sync();
   combine(nullptr, v_work[0], false, nullptr);
   grid.sync();
@@ -411,7 +405,6 @@ __global__ void __launch_bounds__(kV2Threads, 1) sinkhorn_v2_kernel(const SkPara
     const bool check = (it % p.check_every) == 0;
     const bool do_col = !last || check;
     sweep(true, do_col, v_work[cur]);
-    ++sweeps;
     iters = it + 1;
     if (!do_col) break;
     grid.sync();
@@ -430,9 +423,11 @@ __global__ void __launch_bounds__(kV2Threads, 1) sinkhorn_v2_kernel(const SkPara
   }
 
   // ---- drain speculative prefetches so no bulk copy is in flight when the CTA exits ----
-  if (producer && lane == 0) {
-    const long long used = sweeps * nchunks;
-    for (long long c = used; c < issued; ++c) v2_mbar_wait(&full[(int)(c % S)], (uint32_t)(c / S) & 1u);
+  if (tid == 0) {
+    for (long long q = consumed_total; q < issued; ++q) {
+      v2_mbar_wait(&full[c_st], c_par);
+      if (++c_st == S) { c_st = 0; c_par ^= 1u; }
+    }
   }
 
   for (int j = b * kV2Threads + tid; j < n1; j += nblk * kV2Threads)
@@ -453,7 +448,7 @@ template <int KG, int R>
 static int v2_launch_t(SkParams& p, cudaStream_t s) {
   auto kern = sinkhorn_v2_kernel<KG, R>;
   const size_t stage_bytes = (size_t)R * p.n1p * 4;
-  const size_t fixed = (size_t)2 * R * kV2Warps * sizeof(float2) + 2 * 8 * sizeof(uint64_t) + 128;
+  const size_t fixed = (size_t)2 * R * kV2Warps * sizeof(float2) + 8 * sizeof(uint64_t) + 128;
   int S = (int)((220 * 1024 - fixed) / stage_bytes);
   if (S > 8) S = 8;
   if (S < 2) return 1;  // caller falls back to the generic kernel

@@ -234,7 +234,7 @@ class OTPlanSampler:
             ws = _ffi.workspace(L.cfm_plan_sample_workspace_bytes(cp.n0), dev)
             _ffi.check(L.cfm_plan_sample(
                 _ffi.ptr(cp.M), cp.n0, cp.n1, cp.M.stride(0), cp.reg, _ffi.ptr(cp.cost_max),
-                int(cp.normalize), _ffi.ptr(cp.log_u), _ffi.ptr(cp.log_v), _ffi.ptr(u), batch_size,
+                int(cp.normalize), _ffi.ptr(cp.log_u), _ffi.ptr(cp.log_v), 1, _ffi.ptr(u), batch_size,
                 _ffi.ptr(i), _ffi.ptr(j), _ffi.ptr(cp.status), _ffi.ptr(ws), ws.numel(),
                 _ffi.stream_ptr(dev)), "cfm_plan_sample")
         return i, j

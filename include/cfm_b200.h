@@ -106,11 +106,14 @@ int cfm_plan_dot_cost(const float* M, int n0, int n1, int64_t ldm, float reg,
  * The plan is never materialised: entries are recomputed from (M, log_u, log_v).
  * workspace: cfm_plan_sample_workspace_bytes(n0).  If the total mass is < 1e-8 the
  * uniform plan is sampled instead and CFM_FLAG_ZERO_MASS is set (:93-96).
+ * uniform_rows != 0: the potentials come from a solve whose last update was the row update
+ * (always true for cfm_sinkhorn_log_f32), so every row has mass exactly 1/n0: the row-mass
+ * pass is skipped and the within-row inversion runs in fp32 (one launch, two row passes).
  */
 size_t cfm_plan_sample_workspace_bytes(int n0);
 int cfm_plan_sample(const float* M, int n0, int n1, int64_t ldm, float reg,
                     const float* cost_max, int normalize, const double* log_u,
-                    const double* log_v, const double* uniforms, int n_draws,
+                    const double* log_v, int uniform_rows, const double* uniforms, int n_draws,
                     int64_t* i_out, int64_t* j_out, int32_t* status, void* workspace,
                     size_t workspace_bytes, void* stream);
 /* same draw for a dense float64 plan already in device memory (staged parity test) */
