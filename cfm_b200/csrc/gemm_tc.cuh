@@ -4,14 +4,15 @@
 // ONE fp32 TMEM accumulator.  The tensor core's accumulator truncates at each of the 3*K/8
 // accumulate steps, so the result is good to ~1e-6 of sum|a||b| (fp32 FMA: ~1e-7).
 //
-// Persistent warp-specialised kernel, one CTA per SM, 192 threads:
+// Persistent warp-specialised kernel, one CTA per SM, 320 threads:
 //   warp 0   TMA producer: 4 tiled loads per K-chunk (A_hi, A_lo: 128x32 fp32; B_hi, B_lo: 256x32
 //            fp32; 128B swizzle) into a 2-stage smem ring, mbarrier complete_tx.
 //   warp 1   MMA issuer (one elected lane): per K-chunk 4 k-steps x 3 tcgen05.mma (M=128, N=256,
 //            K=8), accumulators in TMEM, double-buffered (2 x 256 columns = all 512) so the epilogue
 //            of tile i overlaps the MMAs of tile i+1; tcgen05.commit frees smem stages / publishes
 //            accumulators.
-//   warps 2-5 epilogue: tcgen05.ld 32x32b.x32 (thread = row, 32 columns per load) handed to the
+//   warps 2-9 epilogue (two per TMEM lane quadrant, half the columns each; two tcgen05.ld 32x32b.x32
+//            in flight per warp; thread = row, 32 columns per load) handed to the
 //            epilogue functor:  begin_row(row, ok); store32(row, col0, acc[32], n_cols); finish(lane).
 // Tile = 128 x 256 outputs; tiles are walked M-fastest so the B panel stays hot in L2.
 // Users: sqdist_tc.cu (cost matrix), mlp_tc.cu (vector-field MLP layers).
@@ -27,14 +28,22 @@ constexpr int kStages = 2;
 constexpr int kABytes = kTM * kTK * 4;         // 16 KB
 constexpr int kBBytes = kTN * kTK * 4;         // 32 KB
 constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;  // 96 KB
-constexpr int kTcThreads = 192;
+constexpr int kEpiWarps = 8;                  // two per TMEM lane quadrant, each takes half the columns
+constexpr int kTcThreads = 64 + 32 * kEpiWarps;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr uint32_t kTmemCols = 512;
 constexpr size_t kTcSmemBytes = (size_t)kStages * kStageBytes + 256;
 
 struct TcShape {
   int n0, n1, d;          // rows of A, rows of B (= output columns), K
   int tiles_m, tiles_n;
+  unsigned long long* dbg;  // optional: 8 globaltimer checkpoints per CTA (CFM_TC_DEBUG), else null
 };
+__device__ __forceinline__ unsigned long long tc_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_MARK(slot) do { if (p.dbg) p.dbg[blockIdx.x * 8 + (slot)] = tc_now(); } while (0)
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -87,6 +96,18 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -135,12 +156,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) TC_MARK(0);  // kernel entry
   const int num_tiles = p.tiles_m * p.tiles_n;
   const int nk = (p.d + kTK - 1) / kTK;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 32 * kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -153,6 +175,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (threadIdx.x == 0) TC_MARK(1);  // barriers initialised, TMEM allocated
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -186,6 +209,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
       for (int kc = 0; kc < nk; ++kc) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
+        if (lane == 0 && kc == 0 && t == (int)blockIdx.x) TC_MARK(2);  // first operand stage landed
         if (lane == 0) {
           const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
           const uint64_t ah = umma_desc_sw128(sa), al = umma_desc_sw128(sa + kABytes);
@@ -208,7 +232,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may touch
+    const int quad = warp & 3;               // TMEM lane quadrant this warp may touch
+    const int half = (warp - 2) >> 2;         // which half of the tile's columns this warp drains
+    constexpr int kColsPerWarp = kTN / (kEpiWarps / 4);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -217,19 +243,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
       epi.begin_row(row, row < p.n0);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kTN);
+      if (warp == 2 && lane == 0 && t == (int)blockIdx.x) TC_MARK(3);  // first accumulator complete
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kTN + half * kColsPerWarp);
 #pragma unroll 1
-      for (int c0 = 0; c0 < kTN; c0 += 32) {
-        uint32_t r[32];
-        tc_ld32(taddr + c0, r);
-        const int col0 = tn * kTN + c0;
-        if (row < p.n0 && col0 < p.n1) epi.store32(row, col0, r, p.n1);
+      for (int c0 = 0; c0 < kColsPerWarp; c0 += 64) {
+        // two 32-column TMEM loads in flight, then both are consumed: twice the ILP per warp
+        uint32_t r0[32], r1[32];
+        tc_ld32_nowait(taddr + c0, r0);
+        tc_ld32_nowait(taddr + c0 + 32, r1);
+        tc_ld_wait();
+        const int col0 = tn * kTN + half * kColsPerWarp + c0;
+        if (row < p.n0 && col0 < p.n1) epi.store32(row, col0, r0, p.n1);
+        if (row < p.n0 && col0 + 32 < p.n1) epi.store32(row, col0 + 32, r1, p.n1);
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
+      if (warp == 2 && lane == 0 && t == (int)blockIdx.x) TC_MARK(4);  // first tile's epilogue done
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     epi.finish(lane);
+    if (warp == 2 && lane == 0) TC_MARK(5);  // all epilogues done
   }
 
   tc_fence_before();
@@ -243,6 +276,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
 // ---- host side -------------------------------------------------------------------------------------
 // (rows, d) fp32 row-major (row stride ld floats) -> box of (box_rows x 32 floats), 128B swizzle, zero OOB fill
 int tc_make_map(CUtensorMap* m, const float* base, int rows, int d, int64_t ld, int box_rows);
+unsigned long long* tc_debug_buffer();  // device buffer set through cfm_tc_debug_buffer(), else null
 // x -> (hi, lo) TF32 split of n contiguous floats (sqdist_tc.cu)
 int tc_split(const float* x, float* hi, float* lo, int64_t n, cudaStream_t s);
 
@@ -259,6 +293,7 @@ inline int launch_gemm_tc(const float* ah, const float* al, int n0, int64_t lda,
   p.n0 = n0; p.n1 = n1; p.d = d;
   p.tiles_m = (n0 + kTM - 1) / kTM;
   p.tiles_n = (n1 + kTN - 1) / kTN;
+  p.dbg = tc_debug_buffer();
   auto kern = gemm_tc_kernel<Epi>;
   CFM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
   int grid = p.tiles_m * p.tiles_n;

@@ -49,4 +49,20 @@ __device__ __forceinline__ float act_apply(float x, int act) {
   return x / (1.f + __expf(-x));  // SiLU
 }
 
+// branch-free variant for the tensor-core epilogue (latency-bound: one warp per scheduler quadrant).
+// SELU negative branch: expm1 by ex2 for x < -0.125 and a degree-5 Taylor polynomial near zero
+// (|rel err| < 1e-6 on both pieces); SiLU through one ex2 and one fast reciprocal.
+__device__ __forceinline__ float act_apply_fast(float x, int act) {
+  if (act == CFM_ACT_SELU) {
+    const float scale = 1.0507009873554804934193349852946f;
+    const float negcoef = (float)(1.6732632423543772848170429916717 * 1.0507009873554804934193349852946);
+    const float xn = fminf(x, 0.f);
+    const float big = ex2f(xn * kLog2e) - 1.f;
+    const float p = xn * fmaf(xn, fmaf(xn, fmaf(xn, fmaf(xn, 1.f / 120.f, 1.f / 24.f), 1.f / 6.f), 0.5f), 1.f);
+    const float em1 = xn > -0.125f ? p : big;
+    return x > 0.f ? x * scale : em1 * negcoef;
+  }
+  return __fdividef(x, 1.f + ex2f(-x * kLog2e));
+}
+
 }  // namespace cfm

@@ -24,43 +24,39 @@ struct MlpTcEpilogue {
   int64_t ldo;
   float t;
   __device__ __forceinline__ void begin_row(int, bool) { t = tcol ? (t_dev ? __ldg(t_dev) : t_host) : 0.f; }
+  __device__ __forceinline__ float one(float acc, float b, float tc) const {
+    float v = acc + b;
+    if (tcol) v = fmaf(t, tc, v);
+    return act >= 0 ? act_apply_fast(v, act) : v;
+  }
   __device__ __forceinline__ void store32(int row, int col0, const uint32_t (&r)[32], int n1) {
-    float o[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      const int col = col0 + c;
-      float v = 0.f;
-      if (col < n1) {
-        v = __uint_as_float(r[c]) + __ldg(bias + col);
-        if (tcol) v = fmaf(t, __ldg(tcol + col), v);
-        if (act >= 0) v = act_apply(v, act);
-      }
-      o[c] = v;
-    }
     const int64_t base = (int64_t)row * ldo + col0;
-    const bool full = (col0 + 32 <= n1) && ((ldo & 3) == 0);
-    if (out) {
-      if (full) {
+    if ((col0 + 32 <= n1) && ((ldo & 3) == 0)) {
 #pragma unroll
-        for (int c = 0; c < 32; c += 4)
-          *reinterpret_cast<float4*>(out + base + c) = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
-      } else {
-        for (int c = 0; c < 32 && col0 + c < n1; ++c) out[base + c] = o[c];
-      }
-    }
-    if (out_hi) {
-      float h[32], l[32];
-#pragma unroll
-      for (int c = 0; c < 32; ++c) split_tf32(o[c], h[c], l[c]);
-      if (full) {
-#pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          *reinterpret_cast<float4*>(out_hi + base + c) = make_float4(h[c], h[c + 1], h[c + 2], h[c + 3]);
-          *reinterpret_cast<float4*>(out_lo + base + c) = make_float4(l[c], l[c + 1], l[c + 2], l[c + 3]);
+      for (int c = 0; c < 32; c += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + c));
+        float4 tc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tcol) tc4 = __ldg(reinterpret_cast<const float4*>(tcol + col0 + c));
+        float4 o;
+        o.x = one(__uint_as_float(r[c]), b.x, tc4.x); o.y = one(__uint_as_float(r[c + 1]), b.y, tc4.y);
+        o.z = one(__uint_as_float(r[c + 2]), b.z, tc4.z); o.w = one(__uint_as_float(r[c + 3]), b.w, tc4.w);
+        if (out) *reinterpret_cast<float4*>(out + base + c) = o;
+        if (out_hi) {
+          float4 h, l;
+          split_tf32(o.x, h.x, l.x); split_tf32(o.y, h.y, l.y);
+          split_tf32(o.z, h.z, l.z); split_tf32(o.w, h.w, l.w);
+          *reinterpret_cast<float4*>(out_hi + base + c) = h;
+          *reinterpret_cast<float4*>(out_lo + base + c) = l;
         }
-      } else {
-        for (int c = 0; c < 32 && col0 + c < n1; ++c) { out_hi[base + c] = h[c]; out_lo[base + c] = l[c]; }
       }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (col0 + c < n1) {
+          const float v = one(__uint_as_float(r[c]), __ldg(bias + col0 + c), tcol ? __ldg(tcol + col0 + c) : 0.f);
+          if (out) out[base + c] = v;
+          if (out_hi) { float h, l; split_tf32(v, h, l); out_hi[base + c] = h; out_lo[base + c] = l; }
+        }
     }
   }
   __device__ __forceinline__ void finish(int) {}

@@ -194,13 +194,13 @@ __global__ void draw_uniform_rows_kernel(const float* __restrict__ M, int n0, in
                        ex2f(fmaf(m.w, c2, (float)(lv[j + 3] * kLog2ed) - vref)));
   };
   // pass A: row total
-  float part = 0.f;
+  double part = 0.0;  // float64 partial sums: keeps the cdf within ~1e-8 of the float64 reference
   if (vec) {
-    for (int j = lane * 4; j < n1; j += 128) { const float4 w = weight4(j); part += (w.x + w.y) + (w.z + w.w); }
+    for (int j = lane * 4; j < n1; j += 128) { const float4 w = weight4(j); part += (double)((w.x + w.y) + (w.z + w.w)); }
   } else {
-    for (int j = lane; j < n1; j += 32) part += weight(j);
+    for (int j = lane; j < n1; j += 32) part += (double)weight(j);
   }
-  const double total = warp_sum((double)part);
+  const double total = warp_sum(part);
   int jsel = -1;
   if (!(total > 0.0) || !isfinite(total)) {
     if (lane == 0 && status) atomicOr(status, CFM_FLAG_NONFINITE);
@@ -211,13 +211,13 @@ __global__ void draw_uniform_rows_kernel(const float* __restrict__ M, int n0, in
     // pass B: coarse blocks of 1024 columns, then a fine scan inside the block that crosses
     for (int b0 = 0; b0 < n1 && jsel < 0; b0 += 1024) {
       const int bend = min(n1, b0 + 1024);
-      float bp = 0.f;
+      double bp = 0.0;
       if (vec) {
-        for (int j = b0 + lane * 4; j < bend; j += 128) { const float4 w = weight4(j); bp += (w.x + w.y) + (w.z + w.w); }
+        for (int j = b0 + lane * 4; j < bend; j += 128) { const float4 w = weight4(j); bp += (double)((w.x + w.y) + (w.z + w.w)); }
       } else {
-        for (int j = b0 + lane; j < bend; j += 32) bp += weight(j);
+        for (int j = b0 + lane; j < bend; j += 32) bp += (double)weight(j);
       }
-      const double bsum = warp_sum((double)bp);
+      const double bsum = warp_sum(bp);
       if (run + bsum > target || bend == n1) {
         // fine scan: 128 (vec) or 32 (scalar) columns per step, in natural column order
         const int step = vec ? 128 : 32;

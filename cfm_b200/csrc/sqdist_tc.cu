@@ -26,25 +26,31 @@ struct SqDistTcEpilogue {
   int squared;
   float a, tmax;
   __device__ __forceinline__ void begin_row(int row, bool ok) { a = ok ? __ldg(nx + row) : 0.f; }
+  __device__ __forceinline__ float one(float acc, float b) {
+    float v = fmaxf((a + b) - 2.f * acc, 0.f);
+    const float s = __fsqrt_rn(v);
+    return squared ? s * s : s;
+  }
   __device__ __forceinline__ void store32(int row, int col0, const uint32_t (&r)[32], int n1) {
     float* dst = M + (int64_t)row * ldm + col0;
-    float o[32];
+    if (col0 + 32 <= n1) {  // full chunk: float4 loads of |x1|^2 (16B aligned: col0 % 32 == 0), float4 stores
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      const int col = col0 + c;
-      const float b = col < n1 ? __ldg(ny + col) : 0.f;
-      float v = fmaxf((a + b) - 2.f * __uint_as_float(r[c]), 0.f);
-      const float s = __fsqrt_rn(v);
-      v = squared ? s * s : s;
-      o[c] = v;
-      if (col < n1) tmax = fmaxf(tmax, v);
-    }
-    if (col0 + 32 <= n1) {
-#pragma unroll
-      for (int c = 0; c < 32; c += 4)
-        *reinterpret_cast<float4*>(dst + c) = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
+      for (int c = 0; c < 32; c += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(ny + col0 + c));
+        float4 o;
+        o.x = one(__uint_as_float(r[c]), b.x); o.y = one(__uint_as_float(r[c + 1]), b.y);
+        o.z = one(__uint_as_float(r[c + 2]), b.z); o.w = one(__uint_as_float(r[c + 3]), b.w);
+        tmax = fmaxf(tmax, fmaxf(fmaxf(o.x, o.y), fmaxf(o.z, o.w)));
+        *reinterpret_cast<float4*>(dst + c) = o;
+      }
     } else {
-      for (int c = 0; c < 32 && col0 + c < n1; ++c) dst[c] = o[c];
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (col0 + c < n1) {
+          const float v = one(__uint_as_float(r[c]), __ldg(ny + col0 + c));
+          tmax = fmaxf(tmax, v);
+          dst[c] = v;
+        }
     }
   }
   __device__ __forceinline__ void finish(int lane) {
@@ -85,6 +91,9 @@ int tc_make_map(CUtensorMap* m, const float* base, int rows, int d, int64_t ld, 
   return CFM_OK;
 }
 
+static unsigned long long* g_tc_dbg = nullptr;
+unsigned long long* tc_debug_buffer() { return g_tc_dbg; }
+
 int tc_split(const float* x, float* hi, float* lo, int64_t n, cudaStream_t s) {
   int64_t blocks = (n + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 8;
@@ -122,3 +131,10 @@ int sqdist_tc_launch(const float* x0, const float* x1, float* M, int n0, int n1,
 }
 
 }  // namespace cfm
+
+// debugging aid: per-CTA globaltimer checkpoints of the next tcgen05 GEMM launches (8 x u64 per CTA,
+// buffer of at least 8 * sm_count entries; pass NULL to switch off)
+extern "C" int cfm_tc_debug_buffer(unsigned long long* buf) {
+  cfm::g_tc_dbg = buf;
+  return CFM_OK;
+}

@@ -59,6 +59,10 @@ int cfm_sqdist_f32(const float* x0, const float* x1, float* M, int n0, int n1, i
                    int64_t ldm, int squared, float* cost_max, int algo, void* workspace,
                    size_t workspace_bytes, void* stream);
 
+/* profiling aid: per-CTA %globaltimer checkpoints of the following tcgen05 GEMM launches are written
+ * to buf (device, >= 8 * sm_count uint64); NULL switches it off.  Not used on the product path. */
+int cfm_tc_debug_buffer(unsigned long long* buf);
+
 /* ---- (a4) entropic plan: log-domain Sinkhorn on uniform marginals ---------------
  * replaces pot.sinkhorn(a, b, M, reg) as bound at optimal_transport.py:51 and called
  * at :87 (POT algorithm: ot/bregman/_sinkhorn.py::sinkhorn_log; a = b = pot.unif, :79).
