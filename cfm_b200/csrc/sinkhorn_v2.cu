@@ -23,13 +23,14 @@
 //     v are <= span and every product stays within 2^(+-3*span) << 2^127.
 //   * per-CTA column partials -> [cta][n1] workspace -> grid barrier -> sliced combine -> v_new,
 //     marginal error -> grid barrier (identical to sinkhorn.cu).
+#include <stdlib.h>
+
 #include "sinkhorn_common.cuh"
 
 namespace cfm {
 
-constexpr int kV2Consumers = 512;
-constexpr int kV2Threads = kV2Consumers;  // no dedicated producer warp: thread 0 refills after each barrier
-constexpr int kV2Warps = kV2Consumers / 32;
+// NT = threads per CTA (512: one CTA per SM; 256: two CTAs per SM whose barrier domains are
+// independent, so one CTA's per-chunk latency chain is hidden behind the other's work)
 
 __device__ __forceinline__ uint32_t v2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void v2_mbar_init(uint64_t* bar, uint32_t count) {
@@ -56,10 +57,42 @@ __device__ __forceinline__ void v2_bulk_load(void* dst, const void* src, uint32_
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(v2_smem_u32(dst)), "l"(src), "r"(bytes), "r"(v2_smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void v2_consumer_barrier() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+template <int NT>
+__device__ __forceinline__ void v2_consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 
-template <int KG, int R>
-__global__ void __launch_bounds__(kV2Threads, 1) sinkhorn_v2_kernel(const SkParams p, const int S) {
+// Reduce R per-lane values over the warp with a shared shuffle tree: at the stage with offset
+// `off` lanes whose bit `off` is set keep the odd member of each pair, the others the even one, so
+// R values cost R-1 + log2(32/R) shuffles instead of 5R.  On return v[0] holds, in EVERY lane, the
+// warp total of row  multi_row(lane)  (the row's index bits are lane bits 4, 3, 2 for R = 2, 4, 8).
+template <int R>
+__device__ __forceinline__ void multi_reduce(float (&v)[R], int lane) {
+  static_assert(R == 1 || R == 2 || R == 4 || R == 8, "R must be a power of two <= 8");
+  int off = 16;
+#pragma unroll
+  for (int n = R; n > 1; n >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float a = v[2 * i], b = v[2 * i + 1];
+      const float send = upper ? a : b, keep = upper ? b : a;
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+    off >>= 1;
+  }
+  for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+}
+template <int R>
+__device__ __forceinline__ int multi_row(int lane) {
+  int r = 0, bit = 4;
+#pragma unroll
+  for (int n = R, sh = 0; n > 1; n >>= 1, ++sh, --bit) r |= ((lane >> bit) & 1) << sh;
+  return r;
+}
+
+template <int NT, int KG, int R>
+__global__ void __launch_bounds__(NT, 512 / NT) sinkhorn_v2_kernel(const SkParams p, const int S) {
+  constexpr int kV2Consumers = NT, kV2Threads = NT, kV2Warps = NT / 32;
+  constexpr bool kVSmem = KG > 4;  // 32 columns per thread: keep V_j in thread-private smem slots
   extern __shared__ __align__(128) unsigned char v2_smem[];
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -77,6 +110,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) sinkhorn_v2_kernel(const SkPara
   float* stages = reinterpret_cast<float*>(v2_smem);
   float2* rowpart = reinterpret_cast<float2*>(stages + (size_t)S * stage_floats);  // [2][R][16]
   uint64_t* full = reinterpret_cast<uint64_t*>(rowpart + 2 * R * kV2Warps);
+  float* V_s = reinterpret_cast<float*>(full + 8);  // n1p floats when kVSmem
   __shared__ double red[kV2Warps];
 
   if (tid == 0) {
@@ -111,6 +145,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) sinkhorn_v2_kernel(const SkPara
 #pragma unroll
   for (int k = 0; k < KG; ++k) gvalid[k] = (tid + kV2Consumers * k) < ng;
   const int tcol = tid * 4;  // first owned column; group k adds 2048*k
+  const bool full_cols = ng == kV2Consumers * KG;  // every thread owns KG valid float4 groups
 
   // thread 0: issue the bulk copies of the next chunk into its (free) stage
   auto issue_next = [&]() {
@@ -133,20 +168,22 @@ __global__ void __launch_bounds__(kV2Threads, 1) sinkhorn_v2_kernel(const SkPara
       // ---------------- factored (kernel-space in registers) sweep ----------------
       const float vref = do_row ? __ldcg(v_cur) : 0.f;
       const float nkap = -kappa;
-      float4 V[KG];
+      float4 V[kVSmem ? 1 : KG];
       float cs[KG][4];
 #pragma unroll
       for (int k = 0; k < KG; ++k) {
-        V[k] = make_float4(0.f, 0.f, 0.f, 0.f);  // idle columns: weight 0
+        float4 vk = make_float4(0.f, 0.f, 0.f, 0.f);  // idle columns: weight 0
         if (gvalid[k]) {
           if (do_row) {
             const float* vp = v_cur + tcol + kV2Consumers * 4 * k;
-            V[k] = make_float4(ex2f(__ldcg(vp) - vref), ex2f(__ldcg(vp + 1) - vref),
-                               ex2f(__ldcg(vp + 2) - vref), ex2f(__ldcg(vp + 3) - vref));
+            vk = make_float4(ex2f(__ldcg(vp) - vref), ex2f(__ldcg(vp + 1) - vref),
+                             ex2f(__ldcg(vp + 2) - vref), ex2f(__ldcg(vp + 3) - vref));
           } else {
-            V[k] = make_float4(1.f, 1.f, 1.f, 1.f);
+            vk = make_float4(1.f, 1.f, 1.f, 1.f);
           }
         }
+        if (kVSmem) *reinterpret_cast<float4*>(V_s + tcol + kV2Consumers * 4 * k) = vk;  // private slot
+        else V[k] = vk;
 #pragma unroll
         for (int c = 0; c < 4; ++c) cs[k][c] = 0.f;
       }
@@ -159,49 +196,77 @@ __global__ void __launch_bounds__(kV2Threads, 1) sinkhorn_v2_kernel(const SkPara
         float2* rp = rowpart + (chunk & 1) * R * kV2Warps;
         v2_mbar_wait(&full[c_st], c_par);
         float4 E[R][KG];
+        if (full_cols && rv == R) {  // common case: no predicates in the hot loop
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const float* srow = sbase + r * n1p;
+          for (int r = 0; r < R; ++r)
 #pragma unroll
-          for (int k = 0; k < KG; ++k) {
-            E[r][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gvalid[k] && r < rv) {
-              const float4 mv = *reinterpret_cast<const float4*>(srow + kV2Consumers * 4 * k);
+            for (int k = 0; k < KG; ++k) {
+              const float4 mv = *reinterpret_cast<const float4*>(sbase + r * n1p + kV2Consumers * 4 * k);
               E[r][k] = make_float4(ex2f(fmaf(mv.x, c2, nkap)), ex2f(fmaf(mv.y, c2, nkap)),
                                     ex2f(fmaf(mv.z, c2, nkap)), ex2f(fmaf(mv.w, c2, nkap)));
+            }
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float* srow = sbase + r * n1p;
+#pragma unroll
+            for (int k = 0; k < KG; ++k) {
+              E[r][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (gvalid[k] && r < rv) {
+                const float4 mv = *reinterpret_cast<const float4*>(srow + kV2Consumers * 4 * k);
+                E[r][k] = make_float4(ex2f(fmaf(mv.x, c2, nkap)), ex2f(fmaf(mv.y, c2, nkap)),
+                                      ex2f(fmaf(mv.z, c2, nkap)), ex2f(fmaf(mv.w, c2, nkap)));
+              }
             }
           }
         }
         if (++c_st == S) { c_st = 0; c_par ^= 1u; }
         if (do_row) {
+          float sr[R];
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             float s = 0.f;
 #pragma unroll
             for (int k = 0; k < KG; ++k) {
-              s = fmaf(E[r][k].x, V[k].x, s); s = fmaf(E[r][k].y, V[k].y, s);
-              s = fmaf(E[r][k].z, V[k].z, s); s = fmaf(E[r][k].w, V[k].w, s);
+              const float4 vk = kVSmem ? *reinterpret_cast<const float4*>(V_s + tcol + kV2Consumers * 4 * k)
+                                       : V[kVSmem ? 0 : k];
+              s = fmaf(E[r][k].x, vk.x, s); s = fmaf(E[r][k].y, vk.y, s);
+              s = fmaf(E[r][k].z, vk.z, s); s = fmaf(E[r][k].w, vk.w, s);
             }
-            s = warp_sum(s);
-            if (lane == 0) rp[r * kV2Warps + warp] = make_float2(s, 0.f);
+            sr[r] = s;
           }
+          multi_reduce<R>(sr, lane);  // lane L now holds the warp total of row multi_row<R>(L)
+          if ((lane & (32 / R - 1)) == 0) rp[multi_row<R>(lane) * kV2Warps + warp] = make_float2(sr[0], 0.f);
         }
         // every warp has now copied its part of the stage into registers: after this barrier the
         // stage is free, so thread 0 refills it with the chunk S positions ahead
-        v2_consumer_barrier();
+        v2_consumer_barrier<NT>();
         if (tid == 0) issue_next();
         float U[R];
         if (do_row) {
+          // fold the 16 per-warp partials: lanes 0-15 take row r, lanes 16-31 row r+1 (one tree for two rows)
 #pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const float pr = lane < kV2Warps ? rp[r * kV2Warps + lane].x : 0.f;
-            const float S_r = warp_sum(pr);
-            const float u2 = loga - (kappa + vref + log2f(S_r));  // lse_r = kappa + vref + log2(S_r)
-            if (!have_uref) { uref = u2; have_uref = true; }       // first row of the slab fixes uref
-            U[r] = r < rv ? ex2f(u2 - uref) : 0.f;  // padding rows: E = 0 and U = 0 (never 0*inf)
-            if (warp == 0 && lane == 0 && r < rv) {
-              u_work[r0 + r] = u2;
-              p.log_u[r0 + r] = (double)u2 * kLn2d;
+          for (int rr = 0; rr < R; rr += 2) {
+            const int myrow = rr + (lane >> 4);
+            float pr = ((R == 1 && lane >= 16) || (lane & 15) >= kV2Warps)
+                           ? 0.f : rp[(R == 1 ? 0 : myrow) * kV2Warps + (lane & 15)].x;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) pr += __shfl_xor_sync(0xffffffffu, pr, o);
+            float Srow[2];
+            Srow[0] = __shfl_sync(0xffffffffu, pr, 0);
+            Srow[1] = __shfl_sync(0xffffffffu, pr, 16);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int r = rr + h;
+              if (r < R) {
+                const float u2 = loga - (kappa + vref + lg2f(Srow[h]));  // lse_r = kappa + vref + log2(S_r)
+                if (!have_uref) { uref = u2; have_uref = true; }         // first row of the slab fixes uref
+                U[r] = r < rv ? ex2f(u2 - uref) : 0.f;  // padding rows: E = 0 and U = 0 (never 0*inf)
+                if (warp == 0 && lane == 0 && r < rv) {
+                  u_work[r0 + r] = u2;
+                  p.log_u[r0 + r] = (double)u2 * kLn2d;
+                }
+              }
             }
           }
         } else {
@@ -277,7 +342,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) sinkhorn_v2_kernel(const SkPara
           if (lane == 0) rp[r * kV2Warps + warp] = make_float2(wm, s);
         }
       }
-      v2_consumer_barrier();
+      v2_consumer_barrier<NT>();
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         u2[r] = 0.f;
@@ -317,7 +382,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) sinkhorn_v2_kernel(const SkPara
       }
       // the stage is read again by the column phase: it is free only once every warp is past this
       // point, which the NEXT chunk's barrier (or the one below for the last chunk) certifies
-      v2_consumer_barrier();
+      v2_consumer_barrier<NT>();
       if (tid == 0) issue_next();
     }
     consumed_total += nchunks;
@@ -339,7 +404,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) sinkhorn_v2_kernel(const SkPara
     const int cpc = (n1 + nblk - 1) / nblk;
     const int c_begin = b * cpc, c_end = min(n1, c_begin + cpc);
     const int sub = tid & 7;
-    for (int j0 = c_begin; j0 < c_end; j0 += (kV2Consumers >> 3)) {
+    for (int j0 = c_begin; j0 < c_end; j0 += (kV2Consumers >> 3)) {  // NT/8 columns per pass
       const int j = j0 + (tid >> 3);
       const bool act = j < c_end;
       float m = -1.0e30f, s = 0.f;
@@ -444,23 +509,27 @@ __global__ void __launch_bounds__(kV2Threads, 1) sinkhorn_v2_kernel(const SkPara
   }
 }
 
-template <int KG, int R>
+template <int NT, int KG, int R>
 static int v2_launch_t(SkParams& p, cudaStream_t s) {
-  auto kern = sinkhorn_v2_kernel<KG, R>;
+  auto kern = sinkhorn_v2_kernel<NT, KG, R>;
+  constexpr int kPerSm = 512 / NT;
   const size_t stage_bytes = (size_t)R * p.n1p * 4;
-  const size_t fixed = (size_t)2 * R * kV2Warps * sizeof(float2) + 8 * sizeof(uint64_t) + 128;
-  int S = (int)((220 * 1024 - fixed) / stage_bytes);
+  const size_t fixed = (size_t)2 * R * (NT / 32) * sizeof(float2) + 8 * sizeof(uint64_t) + 128 +
+                       (KG > 4 ? (size_t)p.n1p * 4 : 0);
+  const size_t budget = (kPerSm == 1 ? 220 : 108) * 1024;
+  if (budget < fixed + 2 * stage_bytes) return 1;
+  int S = (int)((budget - fixed) / stage_bytes);
   if (S > 8) S = 8;
-  if (S < 2) return 1;  // caller falls back to the generic kernel
   const size_t smem = (size_t)S * stage_bytes + fixed;
   CFM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  CFM_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kV2Threads, smem));
+  CFM_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
   if (per_sm < 1) return 1;
-  int grid = sm_count();
+  if (per_sm > kPerSm) per_sm = kPerSm;
+  int grid = sm_count() * per_sm;
   if (grid > p.n0) grid = p.n0;
   void* args[] = {(void*)&p, (void*)&S};
-  CFM_CUDA_OK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(kV2Threads), args, smem, s));
+  CFM_CUDA_OK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(NT), args, smem, s));
   note_launches(1);
   return CFM_OK;
 }
@@ -468,11 +537,24 @@ static int v2_launch_t(SkParams& p, cudaStream_t s) {
 // returns CFM_OK when launched, 1 when this shape is not covered (caller uses sinkhorn.cu), <0 on error
 int sinkhorn_v2_launch(SkParams& p, cudaStream_t s) {
   if (!p.vec || p.n1p > 8192 || p.n1p != p.n1) return 1;
+  static int cfg = -1;  // CFM_SK_CONFIG: 0 heuristic (default), 1 force 512-thread CTAs, 2 force 256-thread CTAs
+  if (cfg < 0) { const char* e = getenv("CFM_SK_CONFIG"); cfg = e ? atoi(e) : 0; }
   const int ng = p.n1p / 4;
-  const int kg = (ng + kV2Consumers - 1) / kV2Consumers;
-  if (kg <= 1) return v2_launch_t<1, 8>(p, s);
-  if (kg <= 2) return v2_launch_t<2, 4>(p, s);
-  return v2_launch_t<4, 2>(p, s);
+  // measured on B200 at N=8192: one 512-thread CTA per SM 5.16 ms / 100 it, two 256-thread CTAs 6.42 ms
+  const bool two_per_sm = cfg == 2;
+  if (two_per_sm) {
+    const int kg = (ng + 255) / 256;
+    int rc = 1;
+    if (kg <= 1) rc = v2_launch_t<256, 1, 8>(p, s);
+    else if (kg <= 2) rc = v2_launch_t<256, 2, 4>(p, s);
+    else if (kg <= 4) rc = v2_launch_t<256, 4, 2>(p, s);
+    else rc = v2_launch_t<256, 8, 1>(p, s);
+    if (rc != 1) return rc;
+  }
+  const int kg = (ng + 511) / 512;
+  if (kg <= 1) return v2_launch_t<512, 1, 8>(p, s);
+  if (kg <= 2) return v2_launch_t<512, 2, 4>(p, s);
+  return v2_launch_t<512, 4, 2>(p, s);
 }
 
 }  // namespace cfm

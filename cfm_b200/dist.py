@@ -21,14 +21,15 @@ def shard_bounds(n, world_size, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def sharded_sample_pairs(sampler, x0_local, x1_local, group=None, gather=True, global_offset=None,
+def sharded_sample_pairs(sampler, x0_local, x1_local, group=None, gather=True, equal_shards=True,
                          pair_fn=None):
     """Per-shard coupling + optional all-gather of the sampled index pairs.
 
     x0_local / x1_local: this rank's shard.  Returns (i_local, j_local) device index tensors into
     the shard and, if ``gather``, also (i_global, j_global): the concatenation over ranks of the
-    pairs offset into the global batch (rank r's rows start at ``global_offset`` = sum of the
-    shard sizes of ranks < r, all-gathered from the shard sizes when not given).
+    pairs offset into the global batch.  ``equal_shards`` (the DDP case: batch_size // world_size
+    rows everywhere, train_cifar10_ddp.py:74) makes rank r's rows start at r * n_local and needs ONE
+    collective per coupling; ragged shards first all-gather the shard sizes.
     ``pair_fn`` (tests only) replaces ``sampler.sample_pairs``.
     """
     fn = pair_fn if pair_fn is not None else sampler.sample_pairs
@@ -37,11 +38,15 @@ def sharded_sample_pairs(sampler, x0_local, x1_local, group=None, gather=True, g
         return (i, j, i, j) if gather else (i, j)
     ws = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    n_local = torch.tensor([x0_local.shape[0]], dtype=torch.int64, device=i.device)
-    sizes = [torch.zeros_like(n_local) for _ in range(ws)]
-    dist.all_gather(sizes, n_local, group=group)
-    sizes = [int(s.item()) for s in sizes]
-    off = sum(sizes[:rank]) if global_offset is None else int(global_offset)
+    n_local = x0_local.shape[0]
+    if equal_shards:
+        sizes = [n_local] * ws
+    else:
+        nl = torch.tensor([n_local], dtype=torch.int64, device=i.device)
+        got = [torch.zeros_like(nl) for _ in range(ws)]
+        dist.all_gather(got, nl, group=group)
+        sizes = [int(s.item()) for s in got]
+    off = sum(sizes[:rank])
     pairs = torch.stack([i + off, j + off])  # (2, n_local) int64, global row numbers
     pad = max(sizes)
     if pairs.shape[1] != pad:  # ragged shards: pad to the largest so every rank sends equal bytes

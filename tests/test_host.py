@@ -178,7 +178,8 @@ def _gloo_worker(rank, world, port, n_local, q):
             idx = torch.arange(a.shape[0])
             return idx, (idx * 7 + rank) % a.shape[0]
 
-        i, j, ig, jg = cdist.sharded_sample_pairs(None, x0, x1, pair_fn=fake_pairs)
+        i, j, ig, jg = cdist.sharded_sample_pairs(None, x0, x1, pair_fn=fake_pairs,
+                                                  equal_shards=len(set(sizes)) == 1)
         q.put((rank, i.tolist(), j.tolist(), ig.tolist(), jg.tolist()))
     finally:
         dist.destroy_process_group()
