@@ -52,7 +52,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(index)], stdout=self.f,
+                                       "-lms", "50", "-i", str(index)], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -202,6 +202,11 @@ def main():
             return cdist.sharded_sample_plan(sampler, x0, x1)
         return sampler.sample_plan(x0, x1)
 
+    # nvidia-smi is started BEFORE the warm-up (its start-up stalls the GPU for a few ms) and keeps
+    # sampling through the timed region
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    if clocks is not None:
+        time.sleep(0.7)  # let nvidia-smi finish initialising NVML before any timed work
     for _ in range(args.warmup):
         step()
     barrier()
@@ -209,7 +214,6 @@ def main():
     # ---- timed region: K steps, device events, barrier + synchronize both sides ----
     sampler.stage_events = []
     launches0 = L.cfm_launch_count()
-    clocks = ClockSampler(local_rank) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()

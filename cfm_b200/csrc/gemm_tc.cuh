@@ -23,15 +23,22 @@
 
 namespace cfm {
 
-constexpr int kTM = 128, kTN = 256, kTK = 32;  // tile rows / cols / K-chunk (32 fp32 = 128 B swizzle atom)
-constexpr int kStages = 2;
+constexpr int kTM = 128, kTK = 32;  // tile rows / K-chunk (32 fp32 = 128 B swizzle atom)
 constexpr int kABytes = kTM * kTK * 4;         // 16 KB
-constexpr int kBBytes = kTN * kTK * 4;         // 32 KB
-constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;  // 96 KB
+// The N-tile (TN) is a template parameter: 256 (2 smem stages of 96 KB; highest operand reuse, used by
+// the cost matrix) or 128 (3 stages of 64 KB; twice the tiles, used by the MLP layers whose N is 256/784)
+template <int TN> struct TcCfg {
+  static constexpr int kBBytes = TN * kTK * 4;
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kStages = TN == 256 ? 2 : 3;
+  static constexpr uint32_t kTmemCols = 2 * TN;  // two accumulator buffers (power of two: 512 / 256)
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 256;
+  // kind::tf32, fp32 accumulate, A and B K-major, M=128, N=TN
+  static constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) |
+                                     ((uint32_t)(kTM >> 4) << 24);
+};
 constexpr int kEpiWarps = 8;                  // two per TMEM lane quadrant, each takes half the columns
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
-constexpr uint32_t kTmemCols = 512;
-constexpr size_t kTcSmemBytes = (size_t)kStages * kStageBytes + 256;
 
 struct TcShape {
   int n0, n1, d;          // rows of A, rows of B (= output columns), K
@@ -131,21 +138,15 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                           // layout type: SWIZZLE_128B
   return d;
 }
-// kind::tf32, fp32 accumulate, A and B K-major, M=128, N=256
-constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTN >> 3) << 17) |
-                                ((uint32_t)(kTM >> 4) << 24);
 
-// hi = x with the low 13 mantissa bits cleared (exactly TF32), lo = tf32(x - hi)
-__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-  lo = __uint_as_float(__float_as_uint(v - hi) & 0xffffe000u);
-}
-
-template <class Epi>
+template <int TN, class Epi>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
                const TcShape p, Epi epi) {
+  constexpr int kTN = TN, kStages = TcCfg<TN>::kStages, kBBytes = TcCfg<TN>::kBBytes;
+  constexpr int kStageBytes = TcCfg<TN>::kStageBytes;
+  constexpr uint32_t kTmemCols = TcCfg<TN>::kTmemCols, kIdescTf32 = TcCfg<TN>::kIdesc;
   extern __shared__ __align__(1024) uint8_t smem[];
   // carve: stages | barriers | tmem ptr
   uint8_t* stage_base = smem;
@@ -280,9 +281,10 @@ unsigned long long* tc_debug_buffer();  // device buffer set through cfm_tc_debu
 // x -> (hi, lo) TF32 split of n contiguous floats (sqdist_tc.cu)
 int tc_split(const float* x, float* hi, float* lo, int64_t n, cudaStream_t s);
 
-template <class Epi>
+template <int TN, class Epi>
 inline int launch_gemm_tc(const float* ah, const float* al, int n0, int64_t lda, const float* bh,
                           const float* bl, int n1, int64_t ldb, int d, Epi epi, cudaStream_t s) {
+  constexpr int kTN = TN;
   CUtensorMap mah, mal, mbh, mbl;
   int rc;
   if ((rc = tc_make_map(&mah, ah, n0, d, lda, kTM)) != CFM_OK) return rc;
@@ -294,11 +296,12 @@ inline int launch_gemm_tc(const float* ah, const float* al, int n0, int64_t lda,
   p.tiles_m = (n0 + kTM - 1) / kTM;
   p.tiles_n = (n1 + kTN - 1) / kTN;
   p.dbg = tc_debug_buffer();
-  auto kern = gemm_tc_kernel<Epi>;
-  CFM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+  auto kern = gemm_tc_kernel<TN, Epi>;
+  constexpr size_t kSmem = TcCfg<TN>::kSmemBytes;
+  CFM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
   int grid = p.tiles_m * p.tiles_n;
   if (grid > sm_count()) grid = sm_count();
-  kern<<<grid, kTcThreads, kTcSmemBytes, s>>>(mah, mal, mbh, mbl, p, epi); ::cfm::note_launches(1);
+  kern<<<grid, kTcThreads, kSmem, s>>>(mah, mal, mbh, mbl, p, epi); ::cfm::note_launches(1);
   CFM_CUDA_OK(cudaGetLastError());
   return CFM_OK;
 }

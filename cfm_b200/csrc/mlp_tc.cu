@@ -12,6 +12,8 @@
 
 namespace cfm {
 
+constexpr int kMlpTN = 128;  // N tile of the MLP layers: 2x the tiles of the 256-wide one, 3 smem stages
+
 struct MlpTcEpilogue {
   const float* bias;
   const float* tcol;   // nullable: + t * tcol[col]
@@ -111,12 +113,13 @@ static TcWs tc_ws(int batch, int dim, int w) {
 }
 size_t mlp_tc_workspace_bytes(int batch, int dim, int w, int) { return tc_ws(batch, dim, w).total; }
 
-int mlp_tc_forward(const MlpBlobHeader& h, const void* blob, const float* x, int batch, const float* t_dev,
-                   float t_host, int act, float* y, void* ws, size_t ws_bytes, cudaStream_t s) {
+int mlp_tc_forward(const MlpBlobHeader& h, const void* blob, const float* x, const float* x_hi,
+                   const float* x_lo, int batch, const float* t_dev, float t_host, int act, float* y, void* ws,
+                   size_t ws_bytes, cudaStream_t s) {
   const TcWs W = tc_ws(batch, h.dim, h.w);
   CFM_REQUIRE(ws_bytes >= W.total, "mlp tcgen05: workspace too small (%zu < %zu)", ws_bytes, W.total);
-  CFM_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
-              "mlp tcgen05: x and y must be 16-byte aligned");
+  CFM_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x_hi) | reinterpret_cast<uintptr_t>(x_lo) |
+                reinterpret_cast<uintptr_t>(y)) & 15) == 0, "mlp tcgen05: x and y must be 16-byte aligned");
   const char* B = reinterpret_cast<const char*>(blob);
   const char* T = B + h.off_tc;
   const TcBlob tb = tc_blob(h.dimp, h.w, h.out_dim);
@@ -125,19 +128,24 @@ int mlp_tc_forward(const MlpBlobHeader& h, const void* blob, const float* x, int
   auto G = [&](size_t off) { return reinterpret_cast<const float*>(T + off); };
   auto Wp = [&](size_t off) { return reinterpret_cast<float*>(w + off); };
   int rc;
-  if ((rc = tc_split(x, Wp(W.xh), Wp(W.xl), (int64_t)batch * h.dim, s)) != CFM_OK) return rc;
+  const float* xh = x_hi;
+  const float* xl = x_lo;
+  if (x_hi == nullptr) {  // plain fp32 input: split it here; otherwise the caller already did
+    if ((rc = tc_split(x, Wp(W.xh), Wp(W.xl), (int64_t)batch * h.dim, s)) != CFM_OK) return rc;
+    xh = Wp(W.xh); xl = Wp(W.xl);
+  }
   MlpTcEpilogue e0{F(h.off_b0), h.time_varying ? F(h.off_w0t) : nullptr, t_dev, t_host, act, nullptr,
                    Wp(W.ah), Wp(W.al), (int64_t)h.w, 0.f};
-  if ((rc = launch_gemm_tc(Wp(W.xh), Wp(W.xl), batch, (int64_t)h.dim, G(tb.w0h), G(tb.w0l), h.w,
+  if ((rc = launch_gemm_tc<kMlpTN>(xh, xl, batch, (int64_t)h.dim, G(tb.w0h), G(tb.w0l), h.w,
                            (int64_t)h.dimp, h.dim, e0, s)) != CFM_OK) return rc;
   MlpTcEpilogue e1{F(h.off_b1), nullptr, nullptr, 0.f, act, nullptr, Wp(W.bh), Wp(W.bl), (int64_t)h.w, 0.f};
-  if ((rc = launch_gemm_tc(Wp(W.ah), Wp(W.al), batch, (int64_t)h.w, G(tb.w1h), G(tb.w1l), h.w, (int64_t)h.w,
+  if ((rc = launch_gemm_tc<kMlpTN>(Wp(W.ah), Wp(W.al), batch, (int64_t)h.w, G(tb.w1h), G(tb.w1l), h.w, (int64_t)h.w,
                            h.w, e1, s)) != CFM_OK) return rc;
   MlpTcEpilogue e2{F(h.off_b2), nullptr, nullptr, 0.f, act, nullptr, Wp(W.ah), Wp(W.al), (int64_t)h.w, 0.f};
-  if ((rc = launch_gemm_tc(Wp(W.bh), Wp(W.bl), batch, (int64_t)h.w, G(tb.w2h), G(tb.w2l), h.w, (int64_t)h.w,
+  if ((rc = launch_gemm_tc<kMlpTN>(Wp(W.bh), Wp(W.bl), batch, (int64_t)h.w, G(tb.w2h), G(tb.w2l), h.w, (int64_t)h.w,
                            h.w, e2, s)) != CFM_OK) return rc;
   MlpTcEpilogue e3{F(h.off_b3), nullptr, nullptr, 0.f, -1, y, nullptr, nullptr, (int64_t)h.out_dim, 0.f};
-  return launch_gemm_tc(Wp(W.ah), Wp(W.al), batch, (int64_t)h.w, G(tb.w3h), G(tb.w3l), h.out_dim, (int64_t)h.w,
+  return launch_gemm_tc<kMlpTN>(Wp(W.ah), Wp(W.al), batch, (int64_t)h.w, G(tb.w3h), G(tb.w3l), h.out_dim, (int64_t)h.w,
                         h.w, e3, s);
 }
 

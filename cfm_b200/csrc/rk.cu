@@ -53,6 +53,7 @@ __device__ __forceinline__ double block_sum_to(double v, double* smem32) {
 // xs (stage 1..5) or xnew (stage 6) = x + dt * sum_j a[stage][j] * k_j ; also t_stage = t + c*dt
 __global__ void rk_stage_input_kernel(const cfm_rk_state* __restrict__ st, const float* __restrict__ x,
                                       const float* __restrict__ k, float* __restrict__ out,
+                                      float* __restrict__ out_hi, float* __restrict__ out_lo,
                                       float* __restrict__ t_stage, int64_t numel, int stage) {
   if (st->done) return;
   const float dt = st->dt;
@@ -72,12 +73,20 @@ __global__ void rk_stage_input_kernel(const cfm_rk_state* __restrict__ st, const
         v.z = fmaf(a[j], kk.z, v.z); v.w = fmaf(a[j], kk.w, v.w);
       }
     }
-    reinterpret_cast<float4*>(out)[i] = v;
+    if (out) reinterpret_cast<float4*>(out)[i] = v;
+    if (out_hi) {  // operand pair for the tensor-core MLP: the fp32 stage input is never re-read
+      float4 h, l;
+      split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
+      split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+      reinterpret_cast<float4*>(out_hi)[i] = h;
+      reinterpret_cast<float4*>(out_lo)[i] = l;
+    }
   }
   for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
     float v = x[i];
     for (int j = 0; j < stage; ++j) v = fmaf(a[j], k[(int64_t)j * numel + i], v);
-    out[i] = v;
+    if (out) out[i] = v;
+    if (out_hi) { float h, l; split_tf32(v, h, l); out_hi[i] = h; out_lo[i] = l; }
   }
 }
 
@@ -256,10 +265,14 @@ using namespace cfm;
 #define RK_CHECK(cond) CFM_REQUIRE(cond, "%s: bad argument (" #cond ")", __func__)
 
 extern "C" int cfm_rk_stage_input(const cfm_rk_state* st, const float* x, const float* k, float* out,
-                                  float* t_stage, int64_t numel, int stage, void* stream) {
-  RK_CHECK(st && x && k && out && numel > 0 && stage >= 1 && stage <= 6);
-  RK_CHECK(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(out)) & 15) == 0);
-  rk_stage_input_kernel<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(st, x, k, out, t_stage, numel, stage); ::cfm::note_launches(1);
+                                  float* out_hi, float* out_lo, float* t_stage, int64_t numel, int stage,
+                                  void* stream) {
+  RK_CHECK(st && x && k && (out || out_hi) && numel > 0 && stage >= 1 && stage <= 6);
+  RK_CHECK((out_hi == nullptr) == (out_lo == nullptr));
+  RK_CHECK(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(out) |
+             reinterpret_cast<uintptr_t>(out_hi) | reinterpret_cast<uintptr_t>(out_lo)) & 15) == 0);
+  rk_stage_input_kernel<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(st, x, k, out, out_hi, out_lo, t_stage,
+                                                                         numel, stage); ::cfm::note_launches(1);
   CFM_CUDA_OK(cudaGetLastError());
   return CFM_OK;
 }

@@ -1,6 +1,8 @@
 // tcgen05 cost-matrix path:  M = cdist(x0, x1)**2 with the x0.x1^T contraction on the 5th-gen
 // tensor cores (gemm_tc.cuh, 3xTF32) and the |x0|^2 + |x1|^2 - 2 acc, clamp, sqrt, square, max
 // epilogue fused on the TMEM read-out (reference: torchcfm/optimal_transport.py:84-86).
+#include <stdlib.h>
+
 #include "gemm_tc.cuh"
 
 namespace cfm {
@@ -127,7 +129,10 @@ int sqdist_tc_launch(const float* x0, const float* x1, float* M, int n0, int n1,
   if ((rc = tc_split(x0, ah, al, (int64_t)n0 * d, s)) != CFM_OK) return rc;
   if ((rc = tc_split(x1, bh, bl, (int64_t)n1 * d, s)) != CFM_OK) return rc;
   SqDistTcEpilogue epi{M, ldm, nx, ny, cost_max, squared, 0.f, 0.f};
-  return launch_gemm_tc(ah, al, n0, (int64_t)d, bh, bl, n1, (int64_t)d, d, epi, s);
+  static int tn = -1;  // CFM_TC_TN=128 selects the 128-wide N tile (3 smem stages) for experiments
+  if (tn < 0) { const char* e = getenv("CFM_TC_TN"); tn = e ? atoi(e) : 256; }
+  if (tn == 128) return launch_gemm_tc<128>(ah, al, n0, (int64_t)d, bh, bl, n1, (int64_t)d, d, epi, s);
+  return launch_gemm_tc<256>(ah, al, n0, (int64_t)d, bh, bl, n1, (int64_t)d, d, epi, s);
 }
 
 }  // namespace cfm

@@ -111,6 +111,27 @@ class MLP(torch.nn.Module):
         return self._kernel_forward(x, None, float(t), True, out)
 
 
+    def tc_path(self, batch):
+        """True when vector_field(t, x) for this batch runs on the tensor-core kernels."""
+        if self.mlp_algo == 1 or not self.time_varying:
+            return False
+        return bool(_ffi.lib().cfm_mlp_tc_supported(batch, self.net[0].in_features - 1, self.w, self.out_dim))
+
+    def vector_field_split(self, t_dev, x_hi, x_lo, out):
+        """vector_field for an input already stored as its TF32 operand pair (x = x_hi + x_lo), as the
+        dopri5 stage-input kernel writes it; ``t_dev`` is a 1-element CUDA tensor."""
+        L = _ffi.lib()
+        dev = x_hi.device
+        dim = self.net[0].in_features - 1
+        B = x_hi.shape[0]
+        blob = self._prepared(True, dev)
+        ws = _ffi.workspace(L.cfm_mlp_workspace_bytes(B, dim, self.w, self.out_dim, 2), dev)
+        _ffi.check(L.cfm_mlp_forward_split_f32(
+            _ffi.ptr(blob), _ffi.ptr(x_hi), _ffi.ptr(x_lo), B, dim, self.w, self.out_dim, 1, _ffi.ptr(t_dev), 0.0,
+            self.act, _ffi.ptr(out), _ffi.ptr(ws), ws.numel(), _ffi.stream_ptr(dev)), "cfm_mlp_forward_split_f32")
+        return out
+
+
 class torch_wrapper(torch.nn.Module):
     """Wraps model to torchdyn compatible format (reference torchcfm/utils.py:44-52)."""
 

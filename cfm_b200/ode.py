@@ -46,7 +46,8 @@ class NeuralODE(torch.nn.Module):
         self.solver, self.atol, self.rtol = solver, float(atol), float(rtol)
         self.sensitivity = sensitivity  # irrelevant under no_grad sampling; kept for API parity
         self.stats = {}
-        self.sync_every = 1  # steps enqueued between host reads of the controller state
+        self.use_cuda_graph = True  # replay one captured dopri5 step per iteration
+        self._plans = {}
 
     @torch.no_grad()
     def forward(self, x, t_span):
@@ -84,6 +85,57 @@ class NeuralODE(torch.nn.Module):
         self.stats = {"nfe": len(ts) - 1, "accepted": len(ts) - 1, "rejected": 0}
         return traj
 
+    # -- dopri5 -----------------------------------------------------------------------------
+    def _enqueue_step(self, mlp, P):
+        """One full dopri5 step, enqueued on the current stream without any host round trip."""
+        L = _ffi.lib()
+        sp = _ffi.stream_ptr(P["dev"])
+        stp, x, xnew, xs, k, numel = P["stp"], P["x"], P["xnew"], P["xs"], P["k"], P["numel"]
+        split = P["xs_hi"] is not None
+        for stage in range(1, 7):
+            out = xs if stage < 6 else xnew
+            if split:
+                # the stage input goes straight to the MLP as its TF32 operand pair; only stage 6
+                # (= xnew, needed by the error norm and the commit) is also kept in fp32
+                _ffi.check(L.cfm_rk_stage_input(stp, _ffi.ptr(x), _ffi.ptr(k), _ffi.ptr(out if stage == 6 else None),
+                                                _ffi.ptr(P["xs_hi"]), _ffi.ptr(P["xs_lo"]), _ffi.ptr(P["t_stage"]),
+                                                numel, stage, sp), "cfm_rk_stage_input")
+                mlp.vector_field_split(P["t_stage"], P["xs_hi"], P["xs_lo"], k[stage])
+            else:
+                _ffi.check(L.cfm_rk_stage_input(stp, _ffi.ptr(x), _ffi.ptr(k), _ffi.ptr(out), None, None,
+                                                _ffi.ptr(P["t_stage"]), numel, stage, sp), "cfm_rk_stage_input")
+                mlp.vector_field(P["t_stage"], out, out=k[stage])
+        _ffi.check(L.cfm_rk_error_norm(stp, _ffi.ptr(x), _ffi.ptr(xnew), _ffi.ptr(k), numel, sp),
+                   "cfm_rk_error_norm")
+        _ffi.check(L.cfm_rk_control(stp, _ffi.ptr(P["t_span"]), numel, sp), "cfm_rk_control")
+        _ffi.check(L.cfm_rk_commit(stp, _ffi.ptr(x), _ffi.ptr(xnew), _ffi.ptr(k), _ffi.ptr(P["traj"]),
+                                   numel, sp), "cfm_rk_commit")
+
+    def _plan(self, mlp, B, D, n_span, dev):
+        """Persistent buffers (+ the captured step graph) for one problem shape and weight version."""
+        key = (id(mlp), B, D, n_span, str(dev), mlp._weights_key(), mlp.mlp_algo, mlp.act)
+        P = self._plans.get(key)
+        if P is not None:
+            return P
+        self._plans.clear()  # one live plan: a new shape / new weights retire the old graph
+        st = torch.zeros(ctypes_sizeof_state(), dtype=torch.uint8, device=dev)
+        P = {"dev": dev, "numel": B * D, "st": st, "stp": _ffi.ptr(st),
+             "x": torch.empty((B, D), dtype=torch.float32, device=dev),
+             "xnew": torch.empty((B, D), dtype=torch.float32, device=dev),
+             "xs": torch.empty((B, D), dtype=torch.float32, device=dev),
+             "k": torch.empty((7, B, D), dtype=torch.float32, device=dev),
+             "traj": torch.empty((n_span, B, D), dtype=torch.float32, device=dev),
+             "t_span": torch.empty(n_span, dtype=torch.float32, device=dev),
+             "t_stage": torch.zeros(1, dtype=torch.float32, device=dev),
+             "scratch": torch.zeros(4, dtype=torch.float64, device=dev),
+             "pinned": torch.empty(ctypes_sizeof_state(), dtype=torch.uint8, pin_memory=True),
+             "xs_hi": None, "xs_lo": None, "graph": None}
+        if mlp.tc_path(B):
+            P["xs_hi"] = torch.empty((B, D), dtype=torch.float32, device=dev)
+            P["xs_lo"] = torch.empty((B, D), dtype=torch.float32, device=dev)
+        self._plans[key] = P
+        return P
+
     def _dopri5(self, mlp, x0, t_span):
         L = _ffi.lib()
         dev = x0.device
@@ -92,49 +144,44 @@ class NeuralODE(torch.nn.Module):
         n_span = t_span.numel()
         sp = _ffi.stream_ptr(dev)
         ts_host = t_span.cpu()
-
-        x = x0.clone()
-        xnew = torch.empty_like(x)
-        xs = torch.empty_like(x)
-        k = torch.empty((7, B, D), dtype=torch.float32, device=dev)
-        traj = torch.empty((n_span, B, D), dtype=torch.float32, device=dev)
-        traj[0].copy_(x)
-        t_stage = torch.zeros(1, dtype=torch.float32, device=dev)
-        scratch = torch.zeros(4, dtype=torch.float64, device=dev)
+        P = self._plan(mlp, B, D, n_span, dev)
+        x, k, xs, traj, st, stp = P["x"], P["k"], P["xs"], P["traj"], P["st"], P["stp"]
+        x.copy_(x0)
+        traj[0].copy_(x0)
+        P["t_span"].copy_(t_span)
 
         st_host = _ffi.RkState()
         st_host.t, st_host.t_end = float(ts_host[0]), float(ts_host[-1])
         st_host.atol, st_host.rtol = self.atol, self.rtol
         st_host.n_span, st_host.ckpt, st_host.save_slot = n_span, 1, -1
-        st_bytes = torch.frombuffer(bytearray(bytes(st_host)), dtype=torch.uint8)
-        st = st_bytes.to(dev)
-        stp = _ffi.ptr(st)
+        st.copy_(torch.frombuffer(bytearray(bytes(st_host)), dtype=torch.uint8), non_blocking=False)
 
         # k1 = f(t0, x); Hairer initial step needs one extra evaluation
         mlp.vector_field(st_host.t, x, out=k[0])
-        _ffi.check(L.cfm_rk_init_a(stp, _ffi.ptr(x), _ffi.ptr(k[0]), _ffi.ptr(xs), _ffi.ptr(t_stage),
-                                   _ffi.ptr(scratch), numel, sp), "cfm_rk_init_a")
-        mlp.vector_field(t_stage, xs, out=k[1])
-        _ffi.check(L.cfm_rk_init_b(stp, _ffi.ptr(x), _ffi.ptr(k[0]), _ffi.ptr(k[1]), _ffi.ptr(t_span),
-                                   _ffi.ptr(scratch), numel, sp), "cfm_rk_init_b")
+        _ffi.check(L.cfm_rk_init_a(stp, _ffi.ptr(x), _ffi.ptr(k[0]), _ffi.ptr(xs), _ffi.ptr(P["t_stage"]),
+                                   _ffi.ptr(P["scratch"]), numel, sp), "cfm_rk_init_a")
+        mlp.vector_field(P["t_stage"], xs, out=k[1])
+        _ffi.check(L.cfm_rk_init_b(stp, _ffi.ptr(x), _ffi.ptr(k[0]), _ffi.ptr(k[1]), _ffi.ptr(P["t_span"]),
+                                   _ffi.ptr(P["scratch"]), numel, sp), "cfm_rk_init_b")
 
-        pinned = torch.empty(st.numel(), dtype=torch.uint8, pin_memory=True)
+        if self.use_cuda_graph and P["graph"] is None:
+            # the step is a fixed kernel sequence whose control flow lives in device memory: capture it
+            # once (the eager init above has already loaded every kernel) and replay it per step
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue_step(mlp, P)
+            P["graph"] = g
+
+        pinned = P["pinned"]
         max_steps = 100000
         steps = 0
+        cur = None
         while steps < max_steps:
-            for _ in range(self.sync_every):
-                for stage in range(1, 7):
-                    out = xs if stage < 6 else xnew
-                    _ffi.check(L.cfm_rk_stage_input(stp, _ffi.ptr(x), _ffi.ptr(k), _ffi.ptr(out),
-                                                    _ffi.ptr(t_stage), numel, stage, sp),
-                               "cfm_rk_stage_input")
-                    mlp.vector_field(t_stage, out, out=k[stage])
-                _ffi.check(L.cfm_rk_error_norm(stp, _ffi.ptr(x), _ffi.ptr(xnew), _ffi.ptr(k), numel, sp),
-                           "cfm_rk_error_norm")
-                _ffi.check(L.cfm_rk_control(stp, _ffi.ptr(t_span), numel, sp), "cfm_rk_control")
-                _ffi.check(L.cfm_rk_commit(stp, _ffi.ptr(x), _ffi.ptr(xnew), _ffi.ptr(k),
-                                           _ffi.ptr(traj), numel, sp), "cfm_rk_commit")
-                steps += 1
+            if P["graph"] is not None:
+                P["graph"].replay()
+            else:
+                self._enqueue_step(mlp, P)
+            steps += 1
             pinned.copy_(st, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
             cur = _ffi.RkState.from_buffer_copy(bytes(pinned.numpy().tobytes()))
@@ -143,5 +190,9 @@ class NeuralODE(torch.nn.Module):
         else:
             raise RuntimeError("dopri5: step budget exhausted")
         self.stats = {"nfe": cur.nfe, "accepted": cur.accepted, "rejected": cur.rejected,
-                      "t": cur.t, "last_ratio": cur.ratio}
-        return traj
+                      "t": cur.t, "last_ratio": cur.ratio, "graph": P["graph"] is not None}
+        return traj.clone()
+
+
+def ctypes_sizeof_state():
+    return C.sizeof(_ffi.RkState)

@@ -172,6 +172,15 @@ int cfm_mlp_forward_f32(const void* prepared, const float* x, int batch, int dim
                         int act, float* y, int algo, void* workspace,
                         size_t workspace_bytes, void* stream);
 
+/* Same forward for an input that already exists as its TF32 operand split (x = x_hi + x_lo, as
+ * written by cfm_rk_stage_input); tensor-core path only.  cfm_mlp_tc_supported() != 0 tells whether
+ * a shape runs on it. */
+int cfm_mlp_tc_supported(int batch, int dim, int w, int out_dim);
+int cfm_mlp_forward_split_f32(const void* prepared, const float* x_hi, const float* x_lo, int batch,
+                              int dim, int w, int out_dim, int time_varying, const float* t_dev,
+                              float t_host, int act, float* y, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 /* ---- (a11) dopri5 lock-step driver pieces -------------------------------------------
  * replaces the arithmetic of torchdyn's NeuralODE(solver="dopri5").trajectory (call
  * sites: examples/2D_tutorials/tutorial_training_8_gaussians_to_moons.ipynb:332-338;
@@ -197,9 +206,12 @@ typedef struct cfm_rk_state {
 
 /* stage in 1..5: out = x + dt*sum_j a[stage][j]*k_j (input of stage+1's evaluation);
  * stage 6: the same with the 5th-order weights, i.e. out = xnew (and the FSAL input).
- * *t_stage (device float, nullable) = t + c[stage]*dt. */
+ * out (nullable) receives the fp32 value; out_hi/out_lo (nullable pair) receive its TF32 operand
+ * split, the form cfm_mlp_forward_split_f32 consumes.  *t_stage (device float, nullable) =
+ * t + c[stage]*dt. */
 int cfm_rk_stage_input(const cfm_rk_state* st, const float* x, const float* k, float* out,
-                       float* t_stage, int64_t numel, int stage, void* stream);
+                       float* out_hi, float* out_lo, float* t_stage, int64_t numel, int stage,
+                       void* stream);
 /* st->err_acc += sum((dt*sum_j e_j k_j / (atol + rtol*max(|x|,|xnew|)))^2) */
 int cfm_rk_error_norm(cfm_rk_state* st, const float* x, const float* xnew, const float* k,
                       int64_t numel, void* stream);
