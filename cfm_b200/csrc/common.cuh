@@ -54,6 +54,14 @@ __device__ __forceinline__ float lg2f(float x) {
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// log2 with ~2^-22 ABSOLUTE error for any positive normal x: lg2.approx is only relatively accurate, so
+// it is applied to the mantissa in [1, 2) and the exponent is added exactly
+__device__ __forceinline__ float lg2_abs(float x) {
+  const int b = __float_as_int(x);
+  const float e = (float)((b >> 23) - 127);
+  const float m = __int_as_float((b & 0x007fffff) | 0x3f800000);
+  return e + lg2f(m);
+}
 // streaming 128-bit load: no L1 allocation (data is touched once per sweep from this SM)
 __device__ __forceinline__ float4 ldg_stream4(const float* p) {
   float4 r;

@@ -140,6 +140,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) sinkhorn_v2_kernel(const SkParam
   int c_st = 0;             // consumers: stage of the next chunk to consume
   uint32_t c_par = 0;       //            parity to wait for on full[c_st]
   int p_st = 0, p_chunk = 0;  // producer (thread 0): stage / slab chunk of the next chunk to issue
+  int p_dir = 1;              // sweeps alternate direction (boustrophedon): the rows a sweep ends on are
+                              // the rows the next one starts on, and those are still resident in L2
+  int sweep_no = 0;
   long long issued = 0, consumed_total = 0;
   bool gvalid[KG];
 #pragma unroll
@@ -156,7 +159,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) sinkhorn_v2_kernel(const SkParam
       v2_bulk_load(stages + (size_t)p_st * stage_floats + (size_t)r * n1p,
                    p.M + (int64_t)(r0 + r) * p.ldm, (uint32_t)n1 * 4u, &full[p_st]);
     ++issued;
-    if (++p_chunk == nchunks) p_chunk = 0;
+    p_chunk += p_dir;
+    if (p_chunk == nchunks) { p_chunk = nchunks - 1; p_dir = -1; }   // next sweep runs backwards
+    else if (p_chunk < 0) { p_chunk = 0; p_dir = 1; }
     if (++p_st == S) p_st = 0;
   };
   if (tid == 0)
@@ -189,11 +194,12 @@ __global__ void __launch_bounds__(NT, 512 / NT) sinkhorn_v2_kernel(const SkParam
       }
       float uref = 0.f;
       bool have_uref = !do_row;  // prologue: u = 0 everywhere, U = 1
-      for (int chunk = 0; chunk < nchunks; ++chunk) {
+      for (int cc = 0; cc < nchunks; ++cc) {
+        const int chunk = (sweep_no & 1) ? nchunks - 1 - cc : cc;
         const int r0 = r_begin + chunk * R;
         const int rv = min(R, r_begin + nrows - r0);
         const float* sbase = stages + (uint32_t)c_st * stage_floats + tcol;
-        float2* rp = rowpart + (chunk & 1) * R * kV2Warps;
+        float2* rp = rowpart + (cc & 1) * R * kV2Warps;
         v2_mbar_wait(&full[c_st], c_par);
         float4 E[R][KG];
         if (full_cols && rv == R) {  // common case: no predicates in the hot loop
@@ -259,7 +265,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) sinkhorn_v2_kernel(const SkParam
             for (int h = 0; h < 2; ++h) {
               const int r = rr + h;
               if (r < R) {
-                const float u2 = loga - (kappa + vref + lg2f(Srow[h]));  // lse_r = kappa + vref + log2(S_r)
+                const float u2 = loga - (kappa + vref + lg2_abs(Srow[h]));  // lse_r = kappa + vref + log2(S_r)
                 if (!have_uref) { uref = u2; have_uref = true; }         // first row of the slab fixes uref
                 U[r] = r < rv ? ex2f(u2 - uref) : 0.f;  // padding rows: E = 0 and U = 0 (never 0*inf)
                 if (warp == 0 && lane == 0 && r < rv) {
@@ -284,6 +290,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) sinkhorn_v2_kernel(const SkParam
         }
       }
       consumed_total += nchunks;
+      ++sweep_no;
       if (do_col) {
         // sum_i ex2(M c2 + u_i) over this slab = cs * 2^(kappa + uref): partial (max, sum) form
         const float pm = kappa + uref;
@@ -312,11 +319,12 @@ __global__ void __launch_bounds__(NT, 512 / NT) sinkhorn_v2_kernel(const SkParam
       for (int c = 0; c < 4; ++c) { cm[k][c] = -1.0e30f; cs[k][c] = 0.f; }
     }
     const float inf = __int_as_float(0x7f800000);
-    for (int chunk = 0; chunk < nchunks; ++chunk) {
+    for (int cc = 0; cc < nchunks; ++cc) {
+      const int chunk = (sweep_no & 1) ? nchunks - 1 - cc : cc;
       const int r0 = r_begin + chunk * R;
       const int rv = min(R, r_begin + nrows - r0);
       const float* sbase = stages + (uint32_t)c_st * stage_floats + tcol;
-      float2* rp = rowpart + (chunk & 1) * R * kV2Warps;
+      float2* rp = rowpart + (cc & 1) * R * kV2Warps;
       v2_mbar_wait(&full[c_st], c_par);
       if (++c_st == S) { c_st = 0; c_par ^= 1u; }
       float u2[R];
@@ -386,6 +394,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) sinkhorn_v2_kernel(const SkParam
       if (tid == 0) issue_next();
     }
     consumed_total += nchunks;
+    ++sweep_no;
     if (do_col) {
 #pragma unroll
       for (int k = 0; k < KG; ++k)
