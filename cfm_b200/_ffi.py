@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libcfm_b200.so")
 
 FLAG_NONFINITE, FLAG_ZERO_MASS, FLAG_NOT_CONVERGED, FLAG_INFEASIBLE = 1, 2, 4, 8
 ACT_SELU, ACT_SILU = 0, 1
+FLOW_ICFM, FLOW_TARGET, FLOW_SB, FLOW_VP = 0, 1, 2, 3
 
 
 class CfmLibraryError(RuntimeError):
@@ -54,6 +55,7 @@ SIGNATURES = {
     "cfm_assign_workspace_bytes": (_sz, [_i]),
     "cfm_assign_exact_f32": (_i, [_p, _i, _i64, _p, _i, _p, _p, _p, _p, _sz, _p]),
     "cfm_gather_rows": (_i, [_p, _i64, _i, _p, _i64, _p, _p]),
+    "cfm_flow_pairs_f32": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _i64, _i64, _p]),
     "cfm_mlp_prepared_bytes": (_sz, [_i, _i, _i, _i]),
     "cfm_mlp_prepare": (_i, [_p] * 8 + [_i, _i, _i, _i, _p, _sz, _p]),
     "cfm_mlp_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),

@@ -90,13 +90,12 @@ __global__ void __launch_bounds__(kAsgMaxThreads, 1) assign_kernel(const AsgPara
     v = p.g_v; shortest = p.g_short; path = p.g_path; row4col = p.g_row4col; srlist = p.g_srlist;
     sc = p.g_sc;
   }
-  double* u = p.g_u;
+  // row duals: shared memory too when everything fits (one L2 round trip less per Dijkstra step)
+  double* u = p.use_smem ? reinterpret_cast<double*>(asg_smem + ((size_t)n * 29 + 7) / 8 * 8) : p.g_u;
   int32_t* col4row = p.sigma;
 
-  __shared__ MinKey wkey[32];
-  __shared__ MinKey bkey;
-  __shared__ int s_sink, s_i, s_nsr, s_naug, s_bad;
-  __shared__ double s_minval;
+  __shared__ MinKey wkey[2][32];  // per-warp candidates, double-buffered by step parity
+  __shared__ int s_naug, s_bad, s_steps;
 
   const float cmax = (p.normalize && p.cost_max) ? __ldg(p.cost_max) : 1.f;
   auto cost = [&](int i, int j) -> double {
@@ -107,7 +106,7 @@ __global__ void __launch_bounds__(kAsgMaxThreads, 1) assign_kernel(const AsgPara
 
   // ---- init: v = 0, nothing assigned ----
   for (int j = tid; j < n; j += nt) { v[j] = 0.0; row4col[j] = -1; col4row[j] = -1; }
-  if (tid == 0) { s_naug = 0; s_bad = 0; }
+  if (tid == 0) { s_naug = 0; s_bad = 0; s_steps = 0; }
   __syncthreads();
   // u_i = min_j c_ij ; claim argmin column for the lowest-index row that wants it
   for (int i = warp; i < n; i += nwarps) {
@@ -134,14 +133,19 @@ __global__ void __launch_bounds__(kAsgMaxThreads, 1) assign_kernel(const AsgPara
   __syncthreads();
 
   // ---- augment every free row ----
+  // Every thread tracks (i, minval, sink) redundantly: after ONE block barrier per Dijkstra step each
+  // thread folds the per-warp candidates itself, so no second exchange is needed.  Per-column state
+  // (shortest, path, scanned flag) is owned by the thread that scans the column.
+  int steps_total = 0;
   for (int cur = 0; cur < n; ++cur) {
-    if (col4row[cur] >= 0) continue;  // uniform: col4row read after a barrier by all threads
+    if (col4row[cur] >= 0) continue;  // uniform: col4row is only written before a barrier
     for (int j = tid; j < n; j += nt) { shortest[j] = DBL_MAX; sc[j] = 0; }
-    if (tid == 0) { s_sink = -1; s_i = cur; s_nsr = 0; s_minval = 0.0; }
-    __syncthreads();
-    while (true) {
-      const int i = s_i;
-      const double minval = s_minval;
+    int i = cur, sink = -1, nsr = 0, par = 0;
+    double minval = 0.0;
+    bool bad = false;
+    while (sink < 0) {
+      if (tid == 0) srlist[nsr] = i;
+      ++nsr;
       const double ui = u[i];
       MinKey k{DBL_MAX, 0, 0x7fffffff};
       for (int j = tid; j < n; j += nt) {
@@ -153,51 +157,47 @@ __global__ void __launch_bounds__(kAsgMaxThreads, 1) assign_kernel(const AsgPara
         if (key_less(t, k)) k = t;
       }
       k = warp_argmin(k);
-      if (lane == 0) wkey[warp] = k;
+      if (lane == 0) wkey[par][warp] = k;
       __syncthreads();
-      if (warp == 0) {
-        MinKey t = lane < nwarps ? wkey[lane] : MinKey{DBL_MAX, 0, 0x7fffffff};
-        t = warp_argmin(t);
-        if (lane == 0) {
-          srlist[s_nsr++] = i;
-          if (!(t.val < DBL_MAX) || t.j >= n) {
-            s_bad = 1; s_sink = -2;  // infeasible (inf / nan costs)
-          } else {
-            s_minval = t.val;
-            sc[t.j] = 1;
-            if (row4col[t.j] < 0) s_sink = t.j; else s_i = row4col[t.j];
-          }
-          bkey = t;
-        }
+      MinKey best = wkey[par][0];
+      for (int w = 1; w < nwarps; ++w) {
+        const MinKey t = wkey[par][w];
+        if (key_less(t, best)) best = t;
       }
-      __syncthreads();
-      if (s_sink != -1) break;
+      par ^= 1;
+      ++steps_total;
+      if (!(best.val < DBL_MAX) || best.j >= n) { bad = true; break; }  // infeasible (inf / nan costs)
+      minval = best.val;
+      if ((best.j % nt) == tid) sc[best.j] = 1;  // the owner of that column marks it scanned
+      const int r4c = row4col[best.j];
+      if (r4c < 0) sink = best.j; else i = r4c;
     }
-    if (s_sink < 0) break;  // infeasible
-    const double minval = s_minval;
-    const int nsr = s_nsr;
+    if (bad) { if (tid == 0) s_bad = 1; break; }
+    __syncthreads();  // all scans finished: shortest / sc / srlist are final
     // dual updates (Crouse eq. for u over scanned rows, v over scanned columns)
     for (int q = tid; q < nsr; q += nt) {
-      const int i = srlist[q];
-      if (i == cur) u[i] += minval; else u[i] += minval - shortest[col4row[i]];
+      const int ii = srlist[q];
+      if (ii == cur) u[ii] += minval; else u[ii] += minval - shortest[col4row[ii]];
     }
     for (int j = tid; j < n; j += nt)
       if (sc[j]) v[j] -= minval - shortest[j];
     __syncthreads();
     if (tid == 0) {
-      int j = s_sink;
+      int j = sink;
       while (true) {  // walk the alternating path back to `cur`
-        const int i = path[j];
-        row4col[j] = i;
-        const int jprev = col4row[i];
-        col4row[i] = j;
+        const int ii = path[j];
+        row4col[j] = ii;
+        const int jprev = col4row[ii];
+        col4row[ii] = j;
         j = jprev;
-        if (i == cur) break;
+        if (ii == cur) break;
       }
       s_naug++;
     }
     __syncthreads();
   }
+  if (tid == 0) s_steps = steps_total;
+  __syncthreads();
 
   // ---- outputs ----
   double part = 0.0;
@@ -214,11 +214,12 @@ __global__ void __launch_bounds__(kAsgMaxThreads, 1) assign_kernel(const AsgPara
       *p.total_cost = t;
       p.status[0] = s_bad ? CFM_FLAG_INFEASIBLE : 0;
       p.status[1] = s_naug;
+      p.status[2] = s_steps;
     }
   }
 }
 
-static size_t asg_smem_bytes(int n) { return (size_t)n * (8 + 8 + 4 + 4 + 4 + 1) + 16; }
+static size_t asg_smem_bytes(int n) { return ((size_t)n * 29 + 7) / 8 * 8 + (size_t)n * 8 + 16; }
 
 }  // namespace cfm
 

@@ -137,7 +137,7 @@ int cfm_perm_plan_sample(const int32_t* sigma, const double* stairs, int n,
  * P_sigma / n; this returns sigma (column of each row), solved by a shortest-
  * augmenting-path method in float64 on the fp32 costs (the reference casts M to
  * float64 too).  total_cost (float64[1]) = sum_i M[i, sigma_i] (emd2 * n, :300).
- * status: int32[2] = {flags, augmentations}.
+ * status: int32[3] = {flags, augmentations, Dijkstra steps}.
  */
 size_t cfm_assign_workspace_bytes(int n);
 int cfm_assign_exact_f32(const float* M, int n, int64_t ldm, const float* cost_max,
@@ -150,6 +150,28 @@ int cfm_assign_exact_f32(const float* M, int n, int64_t ldm, const float* cost_m
  */
 int cfm_gather_rows(const void* x, int64_t row_elems, int elem_bytes, const int64_t* idx,
                     int64_t n_idx, void* out, void* stream);
+
+/* ---- (a8) fused pair gather + path sample + conditional flow ------------
+ * replaces x0[i], x1[j] (optimal_transport.py:145) followed by sample_xt /
+ * compute_conditional_flow (conditional_flow_matching.py:104-154; overrides :329-394 target,
+ * :429-478 Schrodinger bridge, :569-618 variance preserving) with one pass:
+ *   reads x0[i_idx[r]], x1[j_idx[r]], eps[r]  ->  writes xt[r], ut[r]      (n rows of row_elems)
+ * i_idx / j_idx NULL = identity pairing.  Per-row coefficient vectors (n floats, computed by the
+ * caller with the reference's own expressions so results stay bit-identical):
+ *   ICFM/OT : row_a = t, row_b = 1 - t                      sigma_t = `sigma`
+ *   TARGET  : row_a = t, row_sigma = row_c = 1 - (1-sigma) t  konst = 1 - sigma
+ *   SB      : row_a = t, row_b = 1 - t, row_sigma = sigma sqrt(t(1-t)), row_c = (1-2t)/(2t(1-t)+1e-8)
+ *   VP      : row_a = cos(pi t / 2), row_b = sin(pi t / 2)    sigma_t = `sigma`, konst = pi / 2
+ * row_sigma NULL = use the scalar `sigma`.  Every element op is an unfused, round-to-nearest fp32 op
+ * in the reference's association order. */
+#define CFM_FLOW_ICFM 0
+#define CFM_FLOW_TARGET 1
+#define CFM_FLOW_SB 2
+#define CFM_FLOW_VP 3
+int cfm_flow_pairs_f32(int kind, const float* x0, const float* x1, const int64_t* i_idx,
+                       const int64_t* j_idx, const float* eps, const float* row_a, const float* row_b,
+                       const float* row_sigma, const float* row_c, float sigma, float konst, float* xt,
+                       float* ut, int64_t n, int64_t row_elems, void* stream);
 
 /* ---- (a9/a10) MLP vector field ----------------------------------------------------
  * replaces torchcfm.models.MLP.forward (torchcfm/models/models.py:20-21) composed with
