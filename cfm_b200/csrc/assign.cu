@@ -159,11 +159,9 @@ __global__ void __launch_bounds__(kAsgMaxThreads, 1) assign_kernel(const AsgPara
       k = warp_argmin(k);
       if (lane == 0) wkey[par][warp] = k;
       __syncthreads();
-      MinKey best = wkey[par][0];
-      for (int w = 1; w < nwarps; ++w) {
-        const MinKey t = wkey[par][w];
-        if (key_less(t, best)) best = t;
-      }
+      // every warp folds the <= 32 per-warp candidates with its own shuffle tree (no second barrier)
+      MinKey best = lane < nwarps ? wkey[par][lane] : MinKey{DBL_MAX, 0, 0x7fffffff};
+      best = warp_argmin(best);
       par ^= 1;
       ++steps_total;
       if (!(best.val < DBL_MAX) || best.j >= n) { bad = true; break; }  // infeasible (inf / nan costs)
