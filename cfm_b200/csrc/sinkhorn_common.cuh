@@ -41,6 +41,7 @@ struct SkParams {
   int vec;          // float4 path usable
   int v_in_smem;
   float l2_resident_frac;  // sinkhorn_v2: share of each slab loaded with L2 evict_last (0: default policy)
+  int dbg_flags;    // sinkhorn_v2 A/B switches (CFM_SK_DBG)
   int run_if;       // 0 always; 1 only when auto-mode resolves to fast; 2 only when it resolves to precise
 };
 

@@ -72,6 +72,23 @@ __device__ __forceinline__ uint64_t v2_policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
+// Minimal grid barrier for the co-resident (cooperatively launched) grid: thread 0 of every CTA
+// releases its CTA's global writes, arrives with one atomic and spins with acquire loads until the
+// running counter reaches `target` (= barrier ordinal * gridDim.x).  Cheaper than
+// cooperative_groups::grid.sync(), which costs ~3 us per call at 148 x 512 threads.
+__device__ __forceinline__ void v2_grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
 template <int NT>
 __device__ __forceinline__ void v2_consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 
@@ -158,6 +175,10 @@ __global__ void __launch_bounds__(NT, 512 / NT) sinkhorn_v2_kernel(const SkParam
   int p_dir = 1;              // sweeps alternate direction (boustrophedon): the rows a sweep ends on are
                               // the rows the next one starts on, and those are still resident in L2
   int sweep_no = 0;
+  unsigned int* gbar = reinterpret_cast<unsigned int*>(p.err_ring + 4);  // zeroed by the launcher
+  unsigned int gbar_n = 0;
+  // measured: cg::grid.sync() gives an 11.3 us per-iteration floor, the hand-rolled v2_grid_barrier 12.3 us
+  auto grid_sync = [&]() { (void)gbar; (void)gbar_n; grid.sync(); };
   long long issued = 0, consumed_total = 0;
   bool gvalid[KG];
 #pragma unroll
@@ -441,20 +462,40 @@ __global__ void __launch_bounds__(NT, 512 / NT) sinkhorn_v2_kernel(const SkParam
       const bool act = j < c_end;
       float m = -1.0e30f, s = 0.f;
       if (act) {
-        for (int c0 = sub; c0 < nblk; c0 += 32) {
-          float mm[4], ss[4];
+        if (p.dbg_flags & 1) {  // A/B: previous 4-wide variant
+          for (int c0 = sub; c0 < nblk; c0 += 32) {
+            float mm[4], ss[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 4; ++q) {
+              const int c = c0 + q * 8;
+              if (c < nblk) {
+                mm[q] = __ldcg(part_m + (int64_t)c * n1p + j);
+                ss[q] = __ldcg(part_s + (int64_t)c * n1p + j);
+              } else { mm[q] = -1.0e30f; ss[q] = 0.f; }
+            }
+            const float bm = fmaxf(fmaxf(fmaxf(mm[0], mm[1]), fmaxf(mm[2], mm[3])), m);
+            float acc = s * ex2f(m - bm);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc += ss[q] * ex2f(mm[q] - bm);
+            s = acc; m = bm;
+          }
+        } else
+        for (int c0 = sub; c0 < nblk; c0 += 64) {  // 8 independent (max, sum) pairs in flight per lane
+          float mm[8], ss[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
             const int c = c0 + q * 8;
             if (c < nblk) {
               mm[q] = __ldcg(part_m + (int64_t)c * n1p + j);
               ss[q] = __ldcg(part_s + (int64_t)c * n1p + j);
             } else { mm[q] = -1.0e30f; ss[q] = 0.f; }
           }
-          const float bm = fmaxf(fmaxf(fmaxf(mm[0], mm[1]), fmaxf(mm[2], mm[3])), m);
+          float bm = m;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) bm = fmaxf(bm, mm[q]);
           float acc = s * ex2f(m - bm);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) acc += ss[q] * ex2f(mm[q] - bm);
+          for (int q = 0; q < 8; ++q) acc += ss[q] * ex2f(mm[q] - bm);
           s = acc; m = bm;
         }
       }
@@ -490,9 +531,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) sinkhorn_v2_kernel(const SkParam
   // ---- prologue: v^0 from u = 0 ----
   if (b == 0 && tid < 4) p.err_ring[tid] = 0.0;
   sweep(false, true, nullptr);
-  grid.sync();
+  grid_sync();
   combine(nullptr, v_work[0], false, nullptr);
-  grid.sync();
+  grid_sync();
 
   int cur = 0, iters = 0;
   bool converged = false;
@@ -504,10 +545,11 @@ __global__ void __launch_bounds__(NT, 512 / NT) sinkhorn_v2_kernel(const SkParam
     sweep(true, do_col, v_work[cur]);
     iters = it + 1;
     if (!do_col) break;
-    grid.sync();
+    grid_sync();
     if (b == 0 && tid == 0) p.err_ring[(it + 2) & 3] = 0.0;
-    combine(v_work[cur], v_work[cur ^ 1], true, &p.err_ring[it & 3]);
-    grid.sync();
+    const bool want_err = check || (p.dbg_flags & 2);
+    combine(v_work[cur], v_work[cur ^ 1], want_err, want_err ? &p.err_ring[it & 3] : nullptr);
+    grid_sync();
     if (check) {
       err = sqrt(__ldcg(&p.err_ring[it & 3]));
       if (err < p.stop_thr) { converged = true; break; }
@@ -561,6 +603,7 @@ static int v2_launch_t(SkParams& p, cudaStream_t s) {
   int grid = sm_count() * per_sm;
   if (grid > p.n0) grid = p.n0;
   void* args[] = {(void*)&p, (void*)&S};
+  CFM_CUDA_OK(cudaMemsetAsync(p.err_ring + 4, 0, 16, s));  // grid-barrier counter
   CFM_CUDA_OK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(NT), args, smem, s));
   note_launches(1);
   return CFM_OK;
@@ -573,6 +616,9 @@ int sinkhorn_v2_launch(SkParams& p, cudaStream_t s) {
   if (l2frac < -1.f) { const char* e = getenv("CFM_SK_L2"); l2frac = e ? (float)atof(e) : 0.15f; }  // measured: 0.1-0.2 best (4.68 ms vs 4.92 ms at 0)
   // only worth it when M does not fit in L2 anyway (it is then fully resident by itself)
   p.l2_resident_frac = ((size_t)p.n0 * p.n1 * 4 > (size_t)100 << 20) ? l2frac : 0.f;
+  static int dbg = -1;  // CFM_SK_DBG: A/B switches (bit0: 4-wide combine loads, bit1: marginal error every iteration)
+  if (dbg < 0) { const char* e = getenv("CFM_SK_DBG"); dbg = e ? atoi(e) : 1; }  // same-box A/B: 4-wide loads 45.6 us/iter, 8-wide 45.9, error every iteration +0.9
+  p.dbg_flags = dbg;
   static int cfg = -1;  // CFM_SK_CONFIG: 0 heuristic (default), 1 force 512-thread CTAs, 2 force 256-thread CTAs
   if (cfg < 0) { const char* e = getenv("CFM_SK_CONFIG"); cfg = e ? atoi(e) : 0; }
   const int ng = p.n1p / 4;
