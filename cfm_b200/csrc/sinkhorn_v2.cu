@@ -224,9 +224,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) sinkhorn_v2_kernel(const SkParam
         float4 vk = make_float4(0.f, 0.f, 0.f, 0.f);  // idle columns: weight 0
         if (gvalid[k]) {
           if (do_row) {
-            const float* vp = v_cur + tcol + kV2Consumers * 4 * k;
-            vk = make_float4(ex2f(__ldcg(vp) - vref), ex2f(__ldcg(vp + 1) - vref),
-                             ex2f(__ldcg(vp + 2) - vref), ex2f(__ldcg(vp + 3) - vref));
+            const float4 vv = __ldcg(reinterpret_cast<const float4*>(v_cur + tcol + kV2Consumers * 4 * k));
+            vk = make_float4(ex2f(vv.x - vref), ex2f(vv.y - vref), ex2f(vv.z - vref), ex2f(vv.w - vref));
           } else {
             vk = make_float4(1.f, 1.f, 1.f, 1.f);
           }
@@ -623,8 +622,8 @@ int sinkhorn_v2_launch(SkParams& p, cudaStream_t s) {
   if (cfg < 0) { const char* e = getenv("CFM_SK_CONFIG"); cfg = e ? atoi(e) : 0; }
   const int ng = p.n1p / 4;
   // measured on B200 at N=8192: one 512-thread CTA per SM 5.16 ms / 100 it, two 256-thread CTAs 6.42 ms
-  const bool two_per_sm = cfg == 2;
-  if (two_per_sm) {
+#ifdef CFM_SK_BUILD_256  // experiment only (measured slower): two 256-thread CTAs per SM
+  if (cfg == 2) {
     const int kg = (ng + 255) / 256;
     int rc = 1;
     if (kg <= 1) rc = v2_launch_t<256, 1, 8>(p, s);
@@ -633,6 +632,7 @@ int sinkhorn_v2_launch(SkParams& p, cudaStream_t s) {
     else rc = v2_launch_t<256, 8, 1>(p, s);
     if (rc != 1) return rc;
   }
+#endif
   const int kg = (ng + 511) / 512;
   if (kg <= 1) return v2_launch_t<512, 1, 8>(p, s);
   if (kg <= 2) return v2_launch_t<512, 2, 4>(p, s);
