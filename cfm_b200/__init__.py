@@ -17,6 +17,6 @@ from .conditional_flow_matching import (ConditionalFlowMatcher,  # noqa: F401
                                         VariancePreservingConditionalFlowMatcher, pad_t_like_x)
 from .models import MLP, torch_wrapper  # noqa: F401
 from .ode import NeuralODE  # noqa: F401
-from .optimal_transport import OTPlanSampler, wasserstein  # noqa: F401
+from .optimal_transport import CouplingStream, OTPlanSampler, wasserstein  # noqa: F401
 
 __version__ = "0.1.0"

@@ -50,6 +50,7 @@ SIGNATURES = {
     "cfm_plan_dot_cost": (_i, [_p, _i, _i, _i64, _f, _p, _i, _p, _p, _p, _p]),
     "cfm_plan_sample_workspace_bytes": (_sz, [_i]),
     "cfm_plan_sample": (_i, [_p, _i, _i, _i64, _f, _p, _i, _p, _p, _i, _p, _i, _p, _p, _p, _p, _sz, _p]),
+    "cfm_plan_sample_rows": (_i, [_p, _i, _i, _i64, _f, _p, _i, _p, _p, _p, _i, _p, _p, _p]),
     "cfm_dense_plan_sample_f64": (_i, [_p, _i, _i, _p, _i, _p, _p, _p, _sz, _p]),
     "cfm_perm_plan_sample": (_i, [_p, _p, _i, _p, _i, _p, _p, _p]),
     "cfm_assign_workspace_bytes": (_sz, [_i]),

@@ -125,7 +125,7 @@ __device__ __forceinline__ void rk_prestep(cfm_rk_state* st, const float* t_span
 }
 
 __global__ void rk_control_kernel(cfm_rk_state* st, const float* __restrict__ t_span, int64_t numel) {
-  if (st->done) return;
+  if (st->done) { st->commit = 0; return; }  // a step enqueued past the end of the interval is a no-op
   const float ratio = (float)sqrt(st->err_acc / (double)numel);
   st->ratio = ratio;
   st->err_acc = 0.0;

@@ -154,7 +154,7 @@ __global__ void draw_kernel(E ent, int n0, int n1, const double* __restrict__ ro
   }
   if (jsel < 0) jsel = jlast_pos >= 0 ? jlast_pos : n1 - 1;  // rounding at the row's end
   if (lane == 0) {
-    i_out[draw] = i;
+    if (i_out) i_out[draw] = i;
     j_out[draw] = jsel;
   }
 }
@@ -169,15 +169,23 @@ __global__ void draw_kernel(E ent, int n0, int n1, const double* __restrict__ ro
 __global__ void draw_uniform_rows_kernel(const float* __restrict__ M, int n0, int n1, int64_t ldm,
                                          float reg, const float* __restrict__ cost_max, int normalize,
                                          const double* __restrict__ lv, const double* __restrict__ uniforms,
-                                         int n_draws, int64_t* __restrict__ i_out,
-                                         int64_t* __restrict__ j_out, int32_t* status) {
+                                         const int64_t* __restrict__ rows, int n_draws,
+                                         int64_t* __restrict__ i_out, int64_t* __restrict__ j_out,
+                                         int32_t* status) {
   const int draw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (draw >= n_draws) return;
   const double u = uniforms[draw];
-  int i = (int)(u * (double)n0);
-  if (i >= n0) i = n0 - 1;
-  const double frac = u * (double)n0 - (double)i;  // position inside row i's cdf cell, in [0, 1)
+  int i;
+  double frac;
+  if (rows != nullptr) {  // row-conditional draw  j ~ pi[i, :] / sum(pi[i, :])  (sample_trajectory, :239-248)
+    i = (int)rows[draw];
+    frac = u;
+  } else {
+    i = (int)(u * (double)n0);
+    if (i >= n0) i = n0 - 1;
+    frac = u * (double)n0 - (double)i;  // position inside row i's cdf cell, in [0, 1)
+  }
   const float scale = normalize ? __ldg(cost_max) : 1.f;
   const float c2 = -kLog2e / (reg * scale);
   const float* row = M + (int64_t)i * ldm;
@@ -259,7 +267,7 @@ __global__ void draw_uniform_rows_kernel(const float* __restrict__ M, int n0, in
     if (jsel < 0) jsel = n1 - 1;
   }
   if (lane == 0) {
-    i_out[draw] = i;
+    if (i_out) i_out[draw] = i;
     j_out[draw] = jsel;
   }
 }
@@ -311,13 +319,27 @@ extern "C" int cfm_plan_sample(const float* M, int n0, int n1, int64_t ldm, floa
   if (uniform_rows) {
     if (n_draws == 0) return CFM_OK;
     draw_uniform_rows_kernel<<<(n_draws + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
-        M, n0, n1, ldm, reg, cost_max, normalize, log_v, uniforms, n_draws, i_out, j_out, status); ::cfm::note_launches(1);
+        M, n0, n1, ldm, reg, cost_max, normalize, log_v, uniforms, nullptr, n_draws, i_out, j_out, status); ::cfm::note_launches(1);
     CFM_CUDA_OK(cudaGetLastError());
     return CFM_OK;
   }
   PotEntry ent{M, ldm, reg, cost_max, normalize, log_u, log_v};
   return sample_common(ent, n0, n1, uniforms, n_draws, i_out, j_out, status, workspace,
                        workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int cfm_plan_sample_rows(const float* M, int n0, int n1, int64_t ldm, float reg,
+                                    const float* cost_max, int normalize, const double* log_v,
+                                    const int64_t* rows, const double* uniforms, int n_draws,
+                                    int64_t* j_out, int32_t* status, void* stream) {
+  CFM_REQUIRE(M && log_v && (n_draws == 0 || (rows && uniforms && j_out)), "cfm_plan_sample_rows: null pointer");
+  CFM_REQUIRE(n0 > 0 && n1 > 0 && ldm >= n1 && n_draws >= 0, "cfm_plan_sample_rows: bad shape");
+  CFM_REQUIRE(!(normalize && !cost_max), "cfm_plan_sample_rows: normalize needs cost_max");
+  if (n_draws == 0) return CFM_OK;
+  draw_uniform_rows_kernel<<<(n_draws + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+      M, n0, n1, ldm, reg, cost_max, normalize, log_v, uniforms, rows, n_draws, nullptr, j_out, status); ::cfm::note_launches(1);
+  CFM_CUDA_OK(cudaGetLastError());
+  return CFM_OK;
 }
 
 extern "C" int cfm_dense_plan_sample_f64(const double* plan, int n0, int n1, const double* uniforms,

@@ -47,6 +47,7 @@ class NeuralODE(torch.nn.Module):
         self.sensitivity = sensitivity  # irrelevant under no_grad sampling; kept for API parity
         self.stats = {}
         self.use_cuda_graph = True  # replay one captured dopri5 step per iteration
+        self.max_burst = 32         # steps enqueued between two host reads of the controller state
         self._plans = {}
 
     @torch.no_grad()
@@ -175,13 +176,19 @@ class NeuralODE(torch.nn.Module):
         pinned = P["pinned"]
         max_steps = 100000
         steps = 0
-        cur = None
+        cur = st_host
         while steps < max_steps:
-            if P["graph"] is not None:
-                P["graph"].replay()
-            else:
-                self._enqueue_step(mlp, P)
-            steps += 1
+            # Steps are enqueued in bursts between host reads of the state.  Every t_span point still to
+            # be recorded costs at least one accepted step (the controller clips dt onto it), so that
+            # many steps can be enqueued without looking; a step enqueued after t_end is a no-op on the
+            # device (done flag), so the bound only has to be safe, not tight.
+            burst = max(1, min(self.max_burst, n_span - int(cur.ckpt)))
+            for _ in range(burst):
+                if P["graph"] is not None:
+                    P["graph"].replay()
+                else:
+                    self._enqueue_step(mlp, P)
+            steps += burst
             pinned.copy_(st, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
             cur = _ffi.RkState.from_buffer_copy(bytes(pinned.numpy().tobytes()))

@@ -214,19 +214,30 @@ class OTPlanSampler:
         self._last_inputs = None
         return cp
 
-    def _draw(self, cp, batch_size):
-        """(a6) inverse-cdf draw on the device from host uniforms of the global NumPy RNG."""
+    def _stairs(self, n, dev):
+        """cdf of the uniform permutation plan, the float64 sequential cumsum np.random.choice
+        forms (:118); cached per (n, device)."""
+        cache = self.__dict__.setdefault("_stairs_cache", {})
+        st = cache.get((n, dev))
+        if st is None:
+            stairs = np.cumsum(np.full(n, 1.0 / n))
+            stairs /= stairs[-1]
+            st = cache[(n, dev)] = torch.from_numpy(stairs).to(dev)
+        return st
+
+    def _draw(self, cp, batch_size, u=None):
+        """(a6) inverse-cdf draw on the device from host uniforms of the global NumPy RNG (``u``: those
+        uniforms already on the device, float64)."""
         L = _ffi.lib()
         dev = cp.M.device
-        u_host = np.random.random_sample(batch_size)  # the stream np.random.choice consumes (:118)
-        u = torch.from_numpy(u_host).to(dev, non_blocking=True)
+        if u is None:
+            u_host = np.random.random_sample(batch_size)  # the stream np.random.choice consumes (:118)
+            u = torch.from_numpy(u_host).to(dev, non_blocking=True)
         i = torch.empty(batch_size, dtype=torch.int64, device=dev)
         j = torch.empty(batch_size, dtype=torch.int64, device=dev)
         if cp.method == "exact":
             n = cp.n0
-            stairs = np.cumsum(np.full(n, 1.0 / n))  # sequential float64 cumsum like np.cumsum (:118)
-            stairs /= stairs[-1]
-            st = torch.from_numpy(stairs).to(dev, non_blocking=True)
+            st = self._stairs(n, dev)
             _ffi.check(L.cfm_perm_plan_sample(_ffi.ptr(cp.sigma), _ffi.ptr(st), n, _ffi.ptr(u),
                                               batch_size, _ffi.ptr(i), _ffi.ptr(j),
                                               _ffi.stream_ptr(dev)), "cfm_perm_plan_sample")
@@ -392,17 +403,45 @@ class OTPlanSampler:
             self._report(cp)
         return out
 
+    def _draw_rows(self, cp, rows, u):
+        """Row-conditional draw  j_k ~ pi[rows[k], :] / sum(pi[rows[k], :])  from device uniforms u."""
+        if cp.method == "exact":
+            return cp.sigma.to(torch.int64)[rows]  # one-hot rows: the draw is sigma[i] whatever u is
+        nxt = torch.empty(rows.shape[0], dtype=torch.int64, device=rows.device)
+        _ffi.check(_ffi.lib().cfm_plan_sample_rows(
+            _ffi.ptr(cp.M), cp.n0, cp.n1, cp.M.stride(0), cp.reg, _ffi.ptr(cp.cost_max),
+            int(cp.normalize), _ffi.ptr(cp.log_v), _ffi.ptr(rows), _ffi.ptr(u), rows.shape[0],
+            _ffi.ptr(nxt), _ffi.ptr(cp.status), _ffi.stream_ptr(rows.device)), "cfm_plan_sample_rows")
+        return nxt
+
     def sample_trajectory(self, X):
-        """OT trajectories across ``times`` populations (reference :221-251): times-1 device
-        couplings; the per-sample categorical draws follow the reference's NumPy loop."""
-        times = X.shape[1]
-        pis = [self.get_map(X[:, t], X[:, t + 1]) for t in range(times - 1)]
-        indices = [np.arange(X.shape[0])]
-        for pi in pis:
-            indices.append(np.array([np.random.choice(pi.shape[1], p=pi[i] / pi[i].sum())
-                                     for i in indices[-1]]))
-        Xh = X.detach().cpu() if torch.is_tensor(X) else X
-        return np.stack([Xh[:, t][indices[t]] for t in range(times)], axis=1)
+        """OT trajectories across ``times`` populations (reference :221-251).  The times-1 couplings
+        and the per-sample conditional draws  j ~ pi_t[i, :] / sum(pi_t[i, :])  run on the device (no
+        plan is materialised, cfm_plan_sample_rows); the uniforms are taken from the global NumPy
+        stream in the reference's order -- all draws of transition t, sample by sample, one
+        ``random_sample`` each, exactly what ``np.random.choice(n, p=...)`` consumes at :244-246.
+        Returns a NumPy array (bs, times, *dim) like the reference's ``np.stack``."""
+        times, n = X.shape[1], X.shape[0]
+        if not torch.is_tensor(X):
+            X = torch.as_tensor(X)
+        device = _pick_device(X)
+        rows = torch.arange(n, dtype=torch.int64, device=device)
+        chain = [rows]
+        # the reference solves every coupling before it draws (:233-236); the solves consume no random
+        # numbers, so solve -> draw -> release per transition gives the same chain with one cost
+        # matrix resident at a time
+        for t in range(times - 1):
+            cp = self._couple(X[:, t], X[:, t + 1], device)
+            u = torch.from_numpy(np.random.random_sample(n)).to(device)
+            nxt = self._draw_rows(cp, rows, u)
+            if self.warn:
+                self._report(cp)
+            rows = nxt
+            chain.append(rows)
+            del cp
+        Xh = X.detach()
+        out = [self._gather(Xh[:, t].contiguous().to(device), chain[t]).cpu().numpy() for t in range(times)]
+        return np.stack(out, axis=1)
 
     # ------------------------------------------------------------------ ot_fn callables
     @staticmethod
@@ -491,3 +530,99 @@ def wasserstein(
     if power == 2:
         ret = math.sqrt(ret)
     return ret
+
+
+class CouplingStream:
+    """Software pipeline over a sequence of HOST minibatches: the upload of batch k+1, the coupling of
+    batch k and the download of batch k-1 run on three CUDA streams, so a training loop that feeds
+    host batches (the reference's DataLoader -> ``sample_plan`` pattern, e.g.
+    examples/images/cifar10/train_cifar10.py:133-140) pays max(copy, compute) per batch instead of
+    their sum.  Results, RNG consumption order (the NumPy global stream, reference :118) and warnings
+    are those of calling ``sampler.sample_plan`` on each batch in submission order.
+
+        stream = CouplingStream(sampler)
+        for x0c, x1c in stream.map(loader):      # loader yields (x0, x1) CPU fp32 tensors
+            ...
+
+    ``submit`` / ``collect`` expose the same thing without the generator.  At most ``depth`` batches
+    are in flight; ``submit`` blocks on the oldest one when the pipeline is full.
+    """
+
+    def __init__(self, sampler, device=None, depth=2):
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        _ffi.require_device()
+        self.sampler = sampler
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.depth = int(depth)
+        self._up = torch.cuda.Stream(self.device)
+        self._run = torch.cuda.Stream(self.device)
+        self._down = torch.cuda.Stream(self.device)
+        self._inflight = []  # FIFO of (done_event, out0_host, out1_host, coupling)
+        self._ready = []     # batches whose download already finished because submit had to make room
+
+    def submit(self, x0, x1):
+        """Enqueue one host batch; returns immediately unless ``depth`` batches are already in flight."""
+        for x in (x0, x1):
+            if not torch.is_tensor(x) or x.is_cuda or x.dtype != torch.float32 or x.requires_grad:
+                raise TypeError("CouplingStream takes CPU float32 tensors that do not require grad; "
+                                "device batches need no pipeline (call sample_plan)")
+        while len(self._inflight) >= self.depth:
+            self._ready.append(self._wait_oldest())
+        s, dev = self.sampler, self.device
+        with torch.cuda.stream(self._up):
+            a = x0.contiguous().to(dev, non_blocking=True)
+            b = x1.contiguous().to(dev, non_blocking=True)
+            # the draw's uniforms: consumed from the NumPy stream now (submission order), uploaded from a
+            # pinned staging copy so that no pageable copy blocks the host behind the running solve
+            u = torch.from_numpy(np.random.random_sample(x0.shape[0])).pin_memory().to(dev, non_blocking=True)
+            uploaded = torch.cuda.Event()
+            uploaded.record(self._up)
+        for t in (a, b, u):
+            t.record_stream(self._run)
+        with torch.cuda.stream(self._run):
+            self._run.wait_event(uploaded)
+            cp = s._couple(a, b, dev)
+            i, j = s._draw(cp, x0.shape[0], u)
+            g0 = s._gather(a, i)
+            g1 = s._gather(b, j)
+            coupled = torch.cuda.Event()
+            coupled.record(self._run)
+        g0.record_stream(self._down)
+        g1.record_stream(self._down)
+        with torch.cuda.stream(self._down):
+            self._down.wait_event(coupled)
+            h0 = torch.empty(g0.shape, dtype=g0.dtype, pin_memory=True)
+            h1 = torch.empty(g1.shape, dtype=g1.dtype, pin_memory=True)
+            h0.copy_(g0, non_blocking=True)
+            h1.copy_(g1, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self._down)
+        self._inflight.append((done, h0, h1, cp))
+
+    def _wait_oldest(self):
+        done, h0, h1, cp = self._inflight.pop(0)
+        done.synchronize()
+        if self.sampler.warn:
+            self.sampler._report(cp)
+        return h0, h1
+
+    def pending(self):
+        return len(self._inflight) + len(self._ready)
+
+    def collect(self):
+        """Coupled (x0[i], x1[j]) of the oldest outstanding batch, as pinned CPU tensors."""
+        if self._ready:
+            return self._ready.pop(0)
+        if not self._inflight:
+            raise RuntimeError("CouplingStream.collect() with nothing submitted")
+        return self._wait_oldest()
+
+    def map(self, batches):
+        """Generator: yields the coupled pair of every (x0, x1) in ``batches``, in order."""
+        for x0, x1 in batches:
+            self.submit(x0, x1)
+            while self.pending() >= self.depth:
+                yield self.collect()
+        while self.pending():
+            yield self.collect()

@@ -120,6 +120,14 @@ int cfm_plan_sample(const float* M, int n0, int n1, int64_t ldm, float reg,
                     const double* log_v, int uniform_rows, const double* uniforms, int n_draws,
                     int64_t* i_out, int64_t* j_out, int32_t* status, void* workspace,
                     size_t workspace_bytes, void* stream);
+/* row-conditional draw, replaces the per-sample loop of OTPlanSampler.sample_trajectory
+ * (optimal_transport.py:239-248: np.random.choice(n1, p=pi[i] / pi[i].sum()) for i in rows):
+ * j_out[k] = searchsorted(cumsum(pi[rows[k], :]) / sum(pi[rows[k], :]), uniforms[k], 'right') with
+ * the plan row recomputed from (M, log_v); log_u cancels in the row normalisation. */
+int cfm_plan_sample_rows(const float* M, int n0, int n1, int64_t ldm, float reg,
+                         const float* cost_max, int normalize, const double* log_v,
+                         const int64_t* rows, const double* uniforms, int n_draws,
+                         int64_t* j_out, int32_t* status, void* stream);
 /* same draw for a dense float64 plan already in device memory (staged parity test) */
 int cfm_dense_plan_sample_f64(const double* plan, int n0, int n1, const double* uniforms,
                               int n_draws, int64_t* i_out, int64_t* j_out,

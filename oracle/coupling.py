@@ -75,6 +75,22 @@ def sample_plan(x0, x1, method="exact", reg=0.05, normalize_cost=False, replace=
     return x0[i], x1[j], i, j
 
 
+def trajectory_chain(X, method="exact", reg=0.05, normalize_cost=False, sinkhorn_method="sinkhorn",
+                     **solver_kw):
+    """optimal_transport.py:221-251 -- chain of per-sample conditional draws across the populations
+    X[:, 0], X[:, 1], ...: all plans first (:233-236), then for every transition one
+    ``np.random.choice(n, p=pi[i] / pi[i].sum())`` per sample, in order (:239-248).  Returns the
+    index chain [(bs,) int arrays] and the stacked (bs, times, *dim) NumPy array (:249-251)."""
+    times = X.shape[1]
+    pis = [solve_plan(cost_matrix(X[:, t], X[:, t + 1], normalize_cost), method, reg, sinkhorn_method,
+                      **solver_kw) for t in range(times - 1)]
+    chain = [np.arange(X.shape[0])]
+    for pi in pis:
+        chain.append(np.array([np.random.choice(pi.shape[1], p=pi[i] / pi[i].sum()) for i in chain[-1]]))
+    Xn = X.detach().cpu().numpy() if torch.is_tensor(X) else np.asarray(X)
+    return chain, np.stack([Xn[:, t][chain[t]] for t in range(times)], axis=1)
+
+
 def assignment(M):
     """optimal_transport.py:179 -- sigma from scipy's exact LSA on float64 costs."""
     from scipy.optimize import linear_sum_assignment

@@ -38,6 +38,11 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_traj():
+    return dict(np.load(os.path.join(os.path.dirname(GOLDEN), "trajectory_vectors.npz")))
+
+
+@pytest.fixture(scope="session")
 def lib_built():
     """Build (incrementally) and return the path of libcfm_b200.so."""
     from cfm_b200 import build
