@@ -395,6 +395,35 @@ def main():
             torch.cuda.synchronize(dev)
             line["ode"]["torch_eager_same_gpu_samples_per_s"] = ODE_B / ((time.perf_counter() - t0) / 3)
 
+        # ---- BASELINE config 1 sampling: the 2-D tutorial model, launch-bound regime ----
+        torch.manual_seed(0)
+        small = cfm_b200.MLP(dim=2, w=64, time_varying=True).to(dev)
+        nsm = cfm_b200.NeuralODE(cfm_b200.torch_wrapper(small), solver="dopri5", atol=1e-4, rtol=1e-4)
+        xs = torch.randn(1024, 2, generator=torch.Generator().manual_seed(7)).to(dev)
+        span100 = torch.linspace(0, 1, 100)
+        for _ in range(3):
+            nsm.trajectory(xs, span100)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            nsm.trajectory(xs, span100)
+        torch.cuda.synchronize(dev)
+        c1_s = (time.perf_counter() - t0) / 20
+        line["ode_c1"] = {"metric": "ODE samples/sec (MLP 3-64-64-64-2 SELU, dopri5 1e-4, B=1024, 100 t_span points)",
+                          "value": world * 1024 / c1_s, "unit": "samples/s", "ms_per_trajectory": c1_s * 1e3,
+                          "nfe": nsm.stats["nfe"], "launches_per_trajectory": 1 if nsm.stats.get("fused") else None}
+        if rank == 0:
+            ref_s = vf.make_mlp(2, w=64, time_varying=True).to(dev)
+            ref_s.load_state_dict(small.state_dict())
+            fs = lambda t, z: vf.wrapped_forward(ref_s, t, z)  # noqa: E731
+            with torch.no_grad():
+                vf.dopri5_trajectory(fs, xs, span100.to(dev))
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                vf.dopri5_trajectory(fs, xs, span100.to(dev))
+                torch.cuda.synchronize(dev)
+            line["ode_c1"]["torch_eager_same_gpu_samples_per_s"] = 1024 / (time.perf_counter() - t0)
+
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only) ----
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)

@@ -70,6 +70,9 @@ SIGNATURES = {
     "cfm_rk_init_a": (_i, [_p, _p, _p, _p, _p, _p, _i64, _p]),
     "cfm_rk_init_b": (_i, [_p, _p, _p, _p, _p, _p, _i64, _p]),
     "cfm_axpy_f32": (_i, [_p, _p, _f, _p, _i64, _p]),
+    "cfm_ode_small_supported": (_i, [_i64, _i, _i, _i]),
+    "cfm_ode_small_workspace_bytes": (_sz, [_i64, _i, _i]),
+    "cfm_ode_small_trajectory_f32": (_i, [_p] * 8 + [_i, _i, _i, _i, _p, _i64, _p, _i, _f, _f, _i, _p, _p, _p, _sz, _p]),
 }
 
 _lock = threading.Lock()

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libcfm_b200.so")
 SOURCES = ["api.cu", "sqdist.cu", "sqdist_tc.cu", "sinkhorn.cu", "sinkhorn_v2.cu", "sample.cu", "assign.cu",
-           "gather.cu", "flow.cu", "mlp.cu", "mlp_tc.cu", "rk.cu"]
+           "gather.cu", "flow.cu", "mlp.cu", "mlp_tc.cu", "rk.cu", "ode_small.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC,-O3,-Wall", "--expt-relaxed-constexpr", "-Xptxas", "-v"]

@@ -48,6 +48,7 @@ class NeuralODE(torch.nn.Module):
         self.stats = {}
         self.use_cuda_graph = True  # replay one captured dopri5 step per iteration
         self.max_burst = 32         # steps enqueued between two host reads of the controller state
+        self.use_fused_small = True  # small MLPs: the whole trajectory in one launch (csrc/ode_small.cu)
         self._plans = {}
 
     @torch.no_grad()
@@ -64,13 +65,43 @@ class NeuralODE(torch.nn.Module):
         shape = x.shape
         x0 = x.detach().reshape(shape[0], -1).float().contiguous()
         t_span = torch.as_tensor(t_span, dtype=torch.float32)
-        if self.solver == "euler":
+        if self.use_fused_small and t_span.numel() >= 2 and _ffi.lib().cfm_ode_small_supported(
+                x0.shape[0], x0.shape[1], mlp.w, mlp.out_dim):
+            out = self._fused_small(mlp, x0, t_span.to(dev).contiguous())
+        elif self.solver == "euler":
             out = self._euler(mlp, x0, t_span)
         else:
             out = self._dopri5(mlp, x0, t_span.to(dev).contiguous())
         return out.reshape(out.shape[0], *shape)
 
     # ------------------------------------------------------------------------------------
+    def _fused_small(self, mlp, x0, t_span):
+        """Launch-bound regime (the 2-D tutorial models): Hairer init, all dopri5 / euler steps, the
+        error norms and the controller in ONE cooperative kernel; one host read at the end."""
+        L = _ffi.lib()
+        dev = x0.device
+        B, D = x0.shape
+        n_span = t_span.numel()
+        ps = []
+        for lin in mlp._linears():
+            for p in (lin.weight, lin.bias):
+                if p.device != dev or p.dtype != torch.float32:
+                    raise _ffi.CfmLibraryError("MLP parameters must be fp32 on the input's CUDA device")
+                ps.append(p.detach().contiguous())
+        traj = torch.empty((n_span, B, D), dtype=torch.float32, device=dev)
+        st = torch.zeros(ctypes_sizeof_state(), dtype=torch.uint8, device=dev)
+        ws = _ffi.workspace(L.cfm_ode_small_workspace_bytes(B, D, mlp.w), dev)
+        _ffi.check(L.cfm_ode_small_trajectory_f32(
+            *[_ffi.ptr(p) for p in ps], D, mlp.w, 1, mlp.act, _ffi.ptr(x0), B, _ffi.ptr(t_span), n_span,
+            self.atol, self.rtol, 1 if self.solver == "euler" else 0, _ffi.ptr(traj), _ffi.ptr(st),
+            _ffi.ptr(ws), ws.numel(), _ffi.stream_ptr(dev)), "cfm_ode_small_trajectory_f32")
+        cur = _ffi.RkState.from_buffer_copy(bytes(st.cpu().numpy().tobytes()))
+        if not cur.done:
+            raise RuntimeError("dopri5: step budget exhausted")
+        self.stats = {"nfe": cur.nfe, "accepted": cur.accepted, "rejected": cur.rejected, "t": cur.t,
+                      "last_ratio": cur.ratio, "graph": False, "fused": True}
+        return traj
+
     def _euler(self, mlp, x, t_span):
         L = _ffi.lib()
         ts = t_span.tolist()

@@ -260,6 +260,26 @@ int cfm_rk_init_b(cfm_rk_state* st, const float* x, const float* f0, const float
 int cfm_axpy_f32(const float* x, const float* k, float h, float* x_out, int64_t numel,
                  void* stream);
 
+/* ---- (f-2) whole-trajectory sampling for small vector-field MLPs, ONE launch -----------------
+ * replaces torchdyn's NeuralODE(...).trajectory(x, t_span) loop for the reference's 2-D tutorial
+ * models (examples/2D_tutorials/tutorial_training_8_gaussians_to_moons.ipynb:332-338: MLP(dim=2,
+ * w=64, time_varying=True), 1024 samples, 100 t_span points; runner/src/models/components/
+ * solver.py:184-199), where a forward is microseconds and per-kernel launch latency dominates.
+ * Weights are passed in torch.nn.Linear layout ([out][in], fp32; W0 is [w][dim + time_varying],
+ * time is the LAST input column as torch_wrapper concatenates it, torchcfm/utils.py:51-52).
+ * solver: 0 dopri5 (same controller semantics as the cfm_rk_* pieces above), 1 euler (one step per
+ * t_span interval).  traj: [n_span][batch][dim].  state_out receives t, nfe, accepted, rejected,
+ * done (done == 0 means the step budget ran out).  supported(): w in {32, 64, 128}, out_dim == dim
+ * and the per-row state fits in shared memory.  workspace: cfm_ode_small_workspace_bytes(). */
+int cfm_ode_small_supported(int64_t batch, int dim, int w, int out_dim);
+size_t cfm_ode_small_workspace_bytes(int64_t batch, int dim, int w);
+int cfm_ode_small_trajectory_f32(const float* W0, const float* b0, const float* W1, const float* b1,
+                                 const float* W2, const float* b2, const float* W3, const float* b3,
+                                 int dim, int w, int time_varying, int act, const float* x0,
+                                 int64_t batch, const float* t_span, int n_span, float atol,
+                                 float rtol, int solver, float* traj, cfm_rk_state* state_out,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

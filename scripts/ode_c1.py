@@ -9,15 +9,15 @@ torch.manual_seed(0)
 mlp = cfm_b200.MLP(dim=2, w=64, time_varying=True).to(dev)
 x = torch.randn(1024, 2, device=dev)
 span = torch.linspace(0, 1, 100)
-for burst in (1, 32):
+for fused in (False, True):
     node = cfm_b200.NeuralODE(cfm_b200.torch_wrapper(mlp), solver="dopri5", atol=1e-4, rtol=1e-4)
-    node.max_burst = burst
+    node.use_fused_small = fused
     for _ in range(3): out = node.trajectory(x, span)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(10): out = node.trajectory(x, span)
     torch.cuda.synchronize()
-    print('burst', burst, 'ms per trajectory', (time.perf_counter() - t0) * 100, node.stats)
+    print('fused', fused, 'ms per trajectory', (time.perf_counter() - t0) * 100, node.stats)
 ref_m = vf.make_mlp(2, w=64, time_varying=True).to(dev)
 ref_m.load_state_dict(mlp.state_dict())
 f = lambda t, z: vf.wrapped_forward(ref_m, t, z)
