@@ -19,6 +19,8 @@
 // (warp shuffles + one smem hop).  No host round trips: sigma stays on the device for the
 // sampling kernel.
 #include <float.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -217,6 +219,204 @@ __global__ void __launch_bounds__(kAsgMaxThreads, 1) assign_kernel(const AsgPara
   }
 }
 
+
+// float64 <-> unsigned 64-bit image with the same ordering (total order, -0 < +0, NaNs at the ends)
+__device__ __forceinline__ unsigned long long dkey(double x) {
+  const long long b = __double_as_longlong(x);
+  return (unsigned long long)b ^ ((unsigned long long)(b >> 63) | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dkey_inv(unsigned long long k) {
+  const unsigned long long b = (k & 0x8000000000000000ull) ? (k ^ 0x8000000000000000ull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+struct IKey {
+  unsigned long long k;  // dkey(shortest): smaller is better
+  unsigned sec;          // (assigned column ? 1 << 24 : 0) | column: free columns first, then lowest index
+};
+__device__ __forceinline__ IKey ikey_min(const IKey& a, const IKey& b) {
+  const bool lt = (b.k < a.k) || (b.k == a.k && b.sec < a.sec);
+  IKey r;
+  r.k = lt ? b.k : a.k;
+  r.sec = lt ? b.sec : a.sec;
+  return r;
+}
+
+// ---- the general fast path (n <= 4096): whole CTA, thread t owns columns t, t + nt, ... (KCB of them) ------
+// Same algorithm, initialisation and tie-breaking as assign_kernel (hence the same sigma), reformulated so that
+// every warp executes as few instructions per Dijkstra step as possible -- a lone warp retires about one
+// instruction every 4-5 cycles here, so the step time IS the per-warp instruction count (measured: a
+// single-warp variant with 8 columns per lane took 1370 cycles per step at n = 256, this kernel ~700, the
+// original block kernel ~2300).  Per-column state (dual v, shortest label, predecessor, scanned / free bits)
+// lives in registers; labels are kept as integer-orderable images of the float64 values (dkey) so that the hot
+// loop is branch-free integer selects -- lanes disagree on every predicate, and divergent float64 compares were
+// the bulk of the old step time; r = (minval - u_i) + (c_ij - v_j) costs two float64 adds per column.
+// per step one cost load + one relaxation per owned column, a three-REDUX warp argmin, ONE block barrier
+// (per-warp candidates are double-buffered by step parity), a second three-REDUX fold that every warp does
+// for itself, and one shared-memory lookup of the matched row.
+template <int KCB>
+__global__ void __launch_bounds__(1024, 1) assign_fast_kernel(const AsgParams p) {
+  extern __shared__ __align__(16) unsigned char asg_smem[];
+  const int n = p.n, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  double* u = reinterpret_cast<double*>(asg_smem);          // n
+  double* sh_s = u + n;                                    // n
+  int32_t* path_s = reinterpret_cast<int32_t*>(sh_s + n);  // n
+  int32_t* c4r = path_s + n;                               // n   col4row
+  int32_t* srlist = c4r + n;                               // n
+  int32_t* r4c_s = srlist + n;                             // n   row4col
+  __shared__ unsigned long long wk[2][32];
+  __shared__ unsigned wsec[2][32];
+  __shared__ double wsum[32];
+  const float cmax = (p.normalize && p.cost_max) ? __ldg(p.cost_max) : 1.f;
+  auto cost = [&](int i, int j) -> double {
+    float m = __ldg(p.M + (int64_t)i * p.ldm + j);
+    if (p.normalize) m = __fdiv_rn(m, cmax);
+    return (double)m;
+  };
+  for (int j = tid; j < n; j += nt) { r4c_s[j] = -1; c4r[j] = -1; }
+  __syncthreads();
+  for (int i = warp; i < n; i += nwarps) {  // u_i = min_j c_ij, preferred column (same keys as assign_kernel)
+    MinKey k{DBL_MAX, 0, 0x7fffffff};
+    for (int j = lane; j < n; j += 32) {
+      MinKey t{cost(i, j), 0, j};
+      if (key_less(t, k)) k = t;
+    }
+    k = warp_argmin(k);
+    if (lane == 0) { u[i] = k.val; path_s[i] = k.j; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 0; i < n; ++i) {
+      const int j = path_s[i];
+      if (j >= 0 && j < n && r4c_s[j] < 0 && isfinite(u[i])) { r4c_s[j] = i; c4r[i] = j; }
+    }
+  }
+  __syncthreads();
+
+  double v[KCB];
+  unsigned long long shk[KCB];
+  int pth[KCB];
+  unsigned padmask = 0, freemask = 0;
+#pragma unroll
+  for (int k = 0; k < KCB; ++k) {
+    const int j = tid + nt * k;
+    v[k] = 0.0;
+    pth[k] = -1;
+    if (j >= n) padmask |= 1u << k;
+    else if (r4c_s[j] < 0) freemask |= 1u << k;
+  }
+  const unsigned long long kmax = dkey(DBL_MAX);
+  int naug = 0, steps_total = 0, par = 0;
+  bool bad = false;
+  for (int cur = 0; cur < n && !bad; ++cur) {
+    if (c4r[cur] >= 0) continue;  // uniform: c4r changes only between barriers
+    unsigned scmask = padmask;
+#pragma unroll
+    for (int k = 0; k < KCB; ++k) shk[k] = kmax;
+    int i = cur, sink = -1, nsr = 0;
+    double minval = 0.0;
+    while (sink < 0) {
+      if (tid == 0) srlist[nsr] = i;
+      ++nsr;
+      const double base = minval - u[i];
+      const float* mrow = p.M + (int64_t)i * p.ldm + tid;
+      float c[KCB];
+#pragma unroll
+      for (int k = 0; k < KCB; ++k) c[k] = (padmask >> k) & 1u ? 0.f : __ldg(mrow + nt * k);
+      IKey best{~0ull, 0xffffffffu};
+#pragma unroll
+      for (int k = 0; k < KCB; ++k) {
+        const bool open = !((scmask >> k) & 1u);
+        float m = c[k];
+        if (p.normalize) m = __fdiv_rn(m, cmax);
+        const double r = base + ((double)m - v[k]);
+        const unsigned long long rk = (r == r) ? dkey(r) : ~0ull;
+        const bool upd = open && (rk < shk[k]);
+        shk[k] = upd ? rk : shk[k];
+        pth[k] = upd ? i : pth[k];
+        IKey t;
+        t.k = open ? shk[k] : ~0ull;
+        t.sec = ((freemask >> k) & 1u ? 0u : (1u << 24)) | (unsigned)(tid + nt * k);
+        best = KCB == 1 ? t : ikey_min(best, t);
+      }
+      {
+        const unsigned hi = (unsigned)(best.k >> 32), lo = (unsigned)best.k;
+        const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+        const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+        const unsigned ms = __reduce_min_sync(0xffffffffu, (hi == mh && lo == ml) ? best.sec : 0xffffffffu);
+        if (lane == 0) { wk[par][warp] = ((unsigned long long)mh << 32) | ml; wsec[par][warp] = ms; }
+      }
+      __syncthreads();
+      {
+        const unsigned long long ck = lane < nwarps ? wk[par][lane] : ~0ull;
+        const unsigned cs = lane < nwarps ? wsec[par][lane] : 0xffffffffu;
+        const unsigned hi = (unsigned)(ck >> 32), lo = (unsigned)ck;
+        const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+        const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+        const unsigned ms = __reduce_min_sync(0xffffffffu, (hi == mh && lo == ml) ? cs : 0xffffffffu);
+        best.k = ((unsigned long long)mh << 32) | ml;
+        best.sec = ms;
+      }
+      par ^= 1;
+      ++steps_total;
+      const int bj = (int)(best.sec & 0xffffffu);
+      if (best.k >= kmax || bj >= n) { bad = true; break; }
+      minval = dkey_inv(best.k);
+      if (KCB == 1) { if (tid == bj) scmask |= 1u; }
+      else if (tid == bj % nt) scmask |= 1u << (bj / nt);
+      if (best.sec >> 24) i = r4c_s[bj]; else sink = bj;
+    }
+    if (bad) break;
+#pragma unroll
+    for (int k = 0; k < KCB; ++k) {
+      const int j = tid + nt * k;
+      if (j < n) { sh_s[j] = dkey_inv(shk[k]); path_s[j] = pth[k]; }
+    }
+    __syncthreads();
+    for (int q = tid; q < nsr; q += nt) {
+      const int ii = srlist[q];
+      if (ii == cur) u[ii] += minval; else u[ii] += minval - sh_s[c4r[ii]];
+    }
+#pragma unroll
+    for (int k = 0; k < KCB; ++k)
+      if (((scmask & ~padmask) >> k) & 1u) v[k] -= minval - dkey_inv(shk[k]);
+    if (tid == sink % nt) freemask &= ~(1u << (sink / nt));
+    __syncthreads();
+    if (tid == 0) {
+      int j = sink;
+      while (true) {
+        const int ii = path_s[j];
+        r4c_s[j] = ii;
+        const int jprev = c4r[ii];
+        c4r[ii] = j;
+        j = jprev;
+        if (ii == cur) break;
+      }
+    }
+    ++naug;
+    __syncthreads();
+  }
+  __syncthreads();
+  double part = 0.0;
+  if (!bad)
+    for (int i = tid; i < n; i += nt) part += cost(i, c4r[i]);
+  part = warp_sum(part);
+  if (lane == 0) wsum[warp] = part;
+  for (int i = tid; i < n; i += nt) p.sigma[i] = c4r[i];
+  __syncthreads();
+  if (warp == 0) {
+    double t = lane < nwarps ? wsum[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) {
+      *p.total_cost = t;
+      p.status[0] = bad ? CFM_FLAG_INFEASIBLE : 0;
+      p.status[1] = naug;
+      p.status[2] = steps_total;
+    }
+  }
+}
+
+static size_t asg_fast_smem_bytes(int n) { return (size_t)n * (8 + 8 + 4 * 4) + 16; }
+
 static size_t asg_smem_bytes(int n) { return ((size_t)n * 29 + 7) / 8 * 8 + (size_t)n * 8 + 16; }
 
 }  // namespace cfm
@@ -250,6 +450,28 @@ extern "C" int cfm_assign_exact_f32(const float* M, int n, int64_t ldm, const fl
   p.g_row4col = reinterpret_cast<int32_t*>(w); w += a4;
   p.g_srlist = reinterpret_cast<int32_t*>(w); w += a4;
   p.g_sc = reinterpret_cast<unsigned char*>(w);
+  static int force_block = -1;  // CFM_ASSIGN_BLOCK=1: always use the block-wide kernel (A/B timing, tests)
+  if (force_block < 0) { const char* e = getenv("CFM_ASSIGN_BLOCK"); force_block = e ? atoi(e) : 0; }
+  if (n <= 4096 && !force_block) {
+    const size_t sb = asg_fast_smem_bytes(n);
+    int nt = ((n + 31) / 32) * 32;
+    if (nt < 64) nt = 64;
+    if (nt > 1024) nt = 1024;
+    const int kcb = (n + nt - 1) / nt;
+    if (kcb == 1) {
+      CFM_CUDA_OK(cudaFuncSetAttribute(assign_fast_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
+      assign_fast_kernel<1><<<1, nt, sb, s>>>(p);
+    } else if (kcb == 2) {
+      CFM_CUDA_OK(cudaFuncSetAttribute(assign_fast_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
+      assign_fast_kernel<2><<<1, nt, sb, s>>>(p);
+    } else {
+      CFM_CUDA_OK(cudaFuncSetAttribute(assign_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
+      assign_fast_kernel<4><<<1, nt, sb, s>>>(p);
+    }
+    ::cfm::note_launches(1);
+    CFM_CUDA_OK(cudaGetLastError());
+    return CFM_OK;
+  }
   const size_t smem = asg_smem_bytes(n);
   p.use_smem = smem <= 200 * 1024;
   const size_t dyn = p.use_smem ? smem : 0;
