@@ -137,6 +137,15 @@ def test_hot_path_refuses_to_run_without_a_gpu():
     m = cfm_b200.MLP(dim=2, time_varying=True)
     with pytest.raises(CfmLibraryError):
         cfm_b200.NeuralODE(cfm_b200.torch_wrapper(m)).trajectory(torch.zeros(4, 2), torch.linspace(0, 1, 2))
+    with pytest.raises(CfmLibraryError):
+        cfm_b200.CouplingStream(OTPlanSampler("sinkhorn"))
+    with pytest.raises(CfmLibraryError):
+        OTPlanSampler("exact").sample_trajectory(torch.randn(8, 3, 2))
+
+
+def test_coupling_stream_argument_contract():
+    with pytest.raises(ValueError):
+        cfm_b200.CouplingStream(OTPlanSampler("exact"), depth=0)
 
 
 def test_compat_alias():
