@@ -13,7 +13,8 @@
 //            accumulators.
 //   warps 2-9 epilogue (two per TMEM lane quadrant, half the columns each; two tcgen05.ld 32x32b.x32
 //            in flight per warp; thread = row, 32 columns per load) handed to the
-//            epilogue functor:  begin_row(row, ok); store32(row, col0, acc[32], n_cols); finish(lane).
+//            epilogue functor:  begin_row(row, ok); store32(row0, lane, col0, acc[32], n_rows, n_cols, tile)
+//            -- called by the whole warp, which writes the chunk coalesced via tc_store_chunk32; finish(lane).
 // Tile = 128 x 256 outputs; tiles are walked M-fastest so the B panel stays hot in L2.
 // Users: sqdist_tc.cu (cost matrix), mlp_tc.cu (vector-field MLP layers).
 #pragma once
@@ -32,7 +33,8 @@ template <int TN> struct TcCfg {
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   static constexpr int kStages = TN == 256 ? 2 : 3;
   static constexpr uint32_t kTmemCols = 2 * TN;  // two accumulator buffers (power of two: 512 / 256)
-  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 256;
+  // + one 32x32 fp32 staging tile per epilogue warp (coalesced read-out, see tc_store_chunk32)
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 256 + 8 * 4096;
   // kind::tf32, fp32 accumulate, A and B K-major, M=128, N=TN
   static constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) |
                                      ((uint32_t)(kTM >> 4) << 24);
@@ -139,6 +141,29 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// Coalesced write of one 32 x 32 fp32 chunk whose ROWS are spread over the lanes (TMEM read-out layout: lane =
+// row, v[] = 32 consecutive columns).  Written straight from that layout a warp store instruction touches 32
+// different 128-byte lines, 16 bytes each, and the LSU becomes the epilogue's bottleneck (~6 us of a 10 us tile
+// epilogue).  Here the chunk is transposed through a per-warp XOR-swizzled shared-memory tile (conflict-free
+// 128-bit accesses both ways), so every store instruction writes 4 full rows x 128 contiguous bytes.
+// out: &D[row0][col0], ld in floats (multiple of 4, 16-byte aligned); rows >= rows_valid are not written.
+__device__ __forceinline__ void tc_store_chunk32(float* tile, const float (&v)[32], float* out, int64_t ld,
+                                                 int rows_valid, int lane) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g)
+    *reinterpret_cast<float4*>(tile + lane * 32 + ((g ^ (lane & 7)) << 2)) =
+        make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+  __syncwarp();
+  const int g = lane & 7;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + (lane >> 3);
+    const float4 q = *reinterpret_cast<const float4*>(tile + r * 32 + ((g ^ (r & 7)) << 2));
+    if (r < rows_valid) *reinterpret_cast<float4*>(out + (int64_t)r * ld + 4 * g) = q;
+  }
+  __syncwarp();
+}
+
 template <int TN, class Epi>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
@@ -155,6 +180,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
   uint64_t* tfull = empty + kStages;   // [2] accumulator ready
   uint64_t* tempty = tfull + 2;        // [2] accumulator drained
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* epi_tiles = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);  // [kEpiWarps][32 * 32]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) TC_MARK(0);  // kernel entry
@@ -240,7 +266,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int tm = t % p.tiles_m, tn = t / p.tiles_m;
-      const int row = tm * kTM + quad * 32 + lane;
+      const int row0 = tm * kTM + quad * 32, row = row0 + lane;
+      float* tile = epi_tiles + (warp - 2) * 1024;
       epi.begin_row(row, row < p.n0);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
@@ -254,8 +281,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
         tc_ld32_nowait(taddr + c0 + 32, r1);
         tc_ld_wait();
         const int col0 = tn * kTN + half * kColsPerWarp + c0;
-        if (row < p.n0 && col0 < p.n1) epi.store32(row, col0, r0, p.n1);
-        if (row < p.n0 && col0 + 32 < p.n1) epi.store32(row, col0 + 32, r1, p.n1);
+        // warp-uniform conditions: the whole warp cooperates on the store of a chunk
+        if (row0 < p.n0 && col0 < p.n1) epi.store32(row0, lane, col0, r0, p.n0, p.n1, tile);
+        if (row0 < p.n0 && col0 + 32 < p.n1) epi.store32(row0, lane, col0 + 32, r1, p.n0, p.n1, tile);
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);

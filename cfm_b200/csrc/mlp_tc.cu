@@ -31,27 +31,31 @@ struct MlpTcEpilogue {
     if (tcol) v = fmaf(t, tc, v);
     return act >= 0 ? act_apply_fast(v, act) : v;
   }
-  __device__ __forceinline__ void store32(int row, int col0, const uint32_t (&r)[32], int n1) {
-    const int64_t base = (int64_t)row * ldo + col0;
+  __device__ __forceinline__ void store32(int row0, int lane, int col0, const uint32_t (&r)[32], int n0, int n1,
+                                          float* tile) {
+    const int row = row0 + lane;
     if ((col0 + 32 <= n1) && ((ldo & 3) == 0)) {
+      float o[32];
 #pragma unroll
       for (int c = 0; c < 32; c += 4) {
         const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + c));
         float4 tc4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (tcol) tc4 = __ldg(reinterpret_cast<const float4*>(tcol + col0 + c));
-        float4 o;
-        o.x = one(__uint_as_float(r[c]), b.x, tc4.x); o.y = one(__uint_as_float(r[c + 1]), b.y, tc4.y);
-        o.z = one(__uint_as_float(r[c + 2]), b.z, tc4.z); o.w = one(__uint_as_float(r[c + 3]), b.w, tc4.w);
-        if (out) *reinterpret_cast<float4*>(out + base + c) = o;
-        if (out_hi) {
-          float4 h, l;
-          split_tf32(o.x, h.x, l.x); split_tf32(o.y, h.y, l.y);
-          split_tf32(o.z, h.z, l.z); split_tf32(o.w, h.w, l.w);
-          *reinterpret_cast<float4*>(out_hi + base + c) = h;
-          *reinterpret_cast<float4*>(out_lo + base + c) = l;
-        }
+        o[c] = one(__uint_as_float(r[c]), b.x, tc4.x); o[c + 1] = one(__uint_as_float(r[c + 1]), b.y, tc4.y);
+        o[c + 2] = one(__uint_as_float(r[c + 2]), b.z, tc4.z); o[c + 3] = one(__uint_as_float(r[c + 3]), b.w, tc4.w);
       }
-    } else {
+      const int64_t base = (int64_t)row0 * ldo + col0;
+      const int rows_valid = n0 - row0;
+      if (out) tc_store_chunk32(tile, o, out + base, ldo, rows_valid, lane);
+      if (out_hi) {
+        float l[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) { float h; split_tf32(o[c], h, l[c]); o[c] = h; }
+        tc_store_chunk32(tile, o, out_hi + base, ldo, rows_valid, lane);
+        tc_store_chunk32(tile, l, out_lo + base, ldo, rows_valid, lane);
+      }
+    } else if (row < n0) {
+      const int64_t base = (int64_t)row * ldo + col0;
 #pragma unroll
       for (int c = 0; c < 32; ++c)
         if (col0 + c < n1) {

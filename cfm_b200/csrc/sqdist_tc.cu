@@ -33,19 +33,24 @@ struct SqDistTcEpilogue {
     const float s = __fsqrt_rn(v);
     return squared ? s * s : s;
   }
-  __device__ __forceinline__ void store32(int row, int col0, const uint32_t (&r)[32], int n1) {
-    float* dst = M + (int64_t)row * ldm + col0;
-    if (col0 + 32 <= n1) {  // full chunk: float4 loads of |x1|^2 (16B aligned: col0 % 32 == 0), float4 stores
+  __device__ __forceinline__ void store32(int row0, int lane, int col0, const uint32_t (&r)[32], int n0, int n1,
+                                          float* tile) {
+    const int row = row0 + lane;
+    const bool ok = row < n0;
+    if (col0 + 32 <= n1) {  // full chunk: float4 loads of |x1|^2 (16B aligned: col0 % 32 == 0), coalesced staged store
+      float o[32];
+      float m = 0.f;
 #pragma unroll
       for (int c = 0; c < 32; c += 4) {
         const float4 b = __ldg(reinterpret_cast<const float4*>(ny + col0 + c));
-        float4 o;
-        o.x = one(__uint_as_float(r[c]), b.x); o.y = one(__uint_as_float(r[c + 1]), b.y);
-        o.z = one(__uint_as_float(r[c + 2]), b.z); o.w = one(__uint_as_float(r[c + 3]), b.w);
-        tmax = fmaxf(tmax, fmaxf(fmaxf(o.x, o.y), fmaxf(o.z, o.w)));
-        *reinterpret_cast<float4*>(dst + c) = o;
+        o[c] = one(__uint_as_float(r[c]), b.x); o[c + 1] = one(__uint_as_float(r[c + 1]), b.y);
+        o[c + 2] = one(__uint_as_float(r[c + 2]), b.z); o[c + 3] = one(__uint_as_float(r[c + 3]), b.w);
+        m = fmaxf(m, fmaxf(fmaxf(o[c], o[c + 1]), fmaxf(o[c + 2], o[c + 3])));
       }
-    } else {
+      if (ok) tmax = fmaxf(tmax, m);
+      tc_store_chunk32(tile, o, M + (int64_t)row0 * ldm + col0, ldm, n0 - row0, lane);
+    } else if (ok) {
+      float* dst = M + (int64_t)row * ldm + col0;
 #pragma unroll
       for (int c = 0; c < 32; ++c)
         if (col0 + c < n1) {
