@@ -271,13 +271,14 @@ class OTPlanSampler:
         return info
 
     @staticmethod
-    def _gather(x, idx_dev):
+    def _gather(x, idx_dev, out=None):
         """(a7) x[idx] on x's device; autograd-preserving torch indexing when x needs grad."""
         if x.requires_grad or not x.is_cuda or x.dtype.itemsize not in (1, 2, 4, 8) \
                 or not x.is_contiguous():
             return x[idx_dev.to(x.device)]
         L = _ffi.lib()
-        out = torch.empty((idx_dev.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        if out is None:
+            out = torch.empty((idx_dev.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
         row = int(np.prod(x.shape[1:])) if x.dim() > 1 else 1
         _ffi.check(L.cfm_gather_rows(_ffi.ptr(x), row, x.dtype.itemsize, _ffi.ptr(idx_dev),
                                      idx_dev.shape[0], _ffi.ptr(out), _ffi.stream_ptr(x.device)),
@@ -560,6 +561,38 @@ class CouplingStream:
         self._down = torch.cuda.Stream(self.device)
         self._inflight = []  # FIFO of (done_event, out0_host, out1_host, coupling)
         self._ready = []     # batches whose download already finished because submit had to make room
+        # Device-side staging lives in a ring of depth + 1 slots that are allocated once per batch shape: a slot
+        # is reused only after its previous batch has been collected, so no allocator call (and no implicit
+        # device synchronisation of a cudaMalloc) sits between two batches in steady state.
+        self._slots = [None] * (self.depth + 1)
+        self._next_slot = 0
+        self._primed = set()
+
+    def _slot(self, x0, x1):
+        k = self._next_slot
+        self._next_slot = (k + 1) % len(self._slots)
+        key = (tuple(x0.shape), tuple(x1.shape))
+        sl = self._slots[k]
+        if sl is None or sl["key"] != key:
+            dev, n = self.device, x0.shape[0]
+            sl = {"key": key,
+                  "a": torch.empty(x0.shape, dtype=torch.float32, device=dev),
+                  "b": torch.empty(x1.shape, dtype=torch.float32, device=dev),
+                  "g0": torch.empty(x0.shape, dtype=torch.float32, device=dev),
+                  "g1": torch.empty((n,) + tuple(x1.shape[1:]), dtype=torch.float32, device=dev),
+                  "u_pin": torch.empty(n, dtype=torch.float64, pin_memory=True),
+                  "u": torch.empty(n, dtype=torch.float64, device=dev)}
+            self._slots[k] = sl
+            if key not in self._primed:
+                # Results are handed out as fresh pinned tensors (the caller owns them).  A pinned block torch has
+                # not cached yet costs a cudaHostAlloc, which waits for the device to go idle and so serialises
+                # the pipeline for the first few batches; grow the cache once, up front, to the number of
+                # results that can be alive at a time (in flight + a few held by the caller).
+                self._primed.add(key)
+                grow = [torch.empty(sh, dtype=torch.float32, pin_memory=True)
+                        for _ in range(self.depth + 3) for sh in (sl["g0"].shape, sl["g1"].shape)]
+                del grow
+        return sl
 
     def submit(self, x0, x1):
         """Enqueue one host batch; returns immediately unless ``depth`` batches are already in flight."""
@@ -570,26 +603,25 @@ class CouplingStream:
         while len(self._inflight) >= self.depth:
             self._ready.append(self._wait_oldest())
         s, dev = self.sampler, self.device
+        sl = self._slot(x0, x1)
+        a, b, u = sl["a"], sl["b"], sl["u"]
+        # the draw's uniforms: consumed from the NumPy stream now (submission order), staged through pinned
+        # memory so that no pageable copy blocks the host behind the running solve
+        sl["u_pin"].copy_(torch.from_numpy(np.random.random_sample(x0.shape[0])))
         with torch.cuda.stream(self._up):
-            a = x0.contiguous().to(dev, non_blocking=True)
-            b = x1.contiguous().to(dev, non_blocking=True)
-            # the draw's uniforms: consumed from the NumPy stream now (submission order), uploaded from a
-            # pinned staging copy so that no pageable copy blocks the host behind the running solve
-            u = torch.from_numpy(np.random.random_sample(x0.shape[0])).pin_memory().to(dev, non_blocking=True)
+            a.copy_(x0, non_blocking=True)
+            b.copy_(x1, non_blocking=True)
+            u.copy_(sl["u_pin"], non_blocking=True)
             uploaded = torch.cuda.Event()
             uploaded.record(self._up)
-        for t in (a, b, u):
-            t.record_stream(self._run)
         with torch.cuda.stream(self._run):
             self._run.wait_event(uploaded)
             cp = s._couple(a, b, dev)
             i, j = s._draw(cp, x0.shape[0], u)
-            g0 = s._gather(a, i)
-            g1 = s._gather(b, j)
+            g0 = s._gather(a, i, sl["g0"])
+            g1 = s._gather(b, j, sl["g1"])
             coupled = torch.cuda.Event()
             coupled.record(self._run)
-        g0.record_stream(self._down)
-        g1.record_stream(self._down)
         with torch.cuda.stream(self._down):
             self._down.wait_event(coupled)
             h0 = torch.empty(g0.shape, dtype=g0.dtype, pin_memory=True)
