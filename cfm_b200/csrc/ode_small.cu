@@ -908,8 +908,8 @@ struct Launch {
 };
 
 static int use_group_kernel() {
-  static int v = -1;  // CFM_ODE_VARIANT=warp selects the one-warp-per-row-pair kernel (A/B, tests)
-  if (v < 0) { const char* e = getenv("CFM_ODE_VARIANT"); v = (e && e[0] == 'w') ? 0 : 1; }
+  static int v = -1;  // CFM_ODE_VARIANT=group / warp selects the kernel (A/B, tests); default below
+  if (v < 0) { const char* e = getenv("CFM_ODE_VARIANT"); v = e ? (e[0] == 'g' ? 1 : 0) : 0; }
   return v;
 }
 
