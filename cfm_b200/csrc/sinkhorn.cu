@@ -22,12 +22,14 @@
 //   * two arithmetic modes chosen on the device: fast (fp32 log2-domain, one FFMA + one ex2 per
 //     element) and precise (float64 potentials, IEEE fp32 division forming -M/reg exactly as
 //     NumPy does, for |M/reg| >> 64 where fp32 exponents lose the answer).
+#include <stdlib.h>
+
 #include "sinkhorn_common.cuh"
 
 namespace cfm {
 
 // ---- row phase: one warp computes LSE_j(x(M_rj, v_j)) for one row ---------------------------
-template <bool P, bool VEC, bool SM>
+template <bool P, bool VEC, bool SM, bool MIX>
 __device__ __forceinline__ typename Tr<P>::pot_t row_lse(const float* __restrict__ row,
                                                          const typename Tr<P>::pot_t* vsrc,
                                                          int n1, int ng,
@@ -60,22 +62,22 @@ __device__ __forceinline__ typename Tr<P>::pot_t row_lse(const float* __restrict
       x[q][2] = xf(c[q].z, pv[q].z); x[q][3] = xf(c[q].w, pv[q].w);
       bm = vmax(bm, vmax(vmax(x[q][0], x[q][1]), vmax(x[q][2], x[q][3])));
     }
-    sum_t acc = s * expdiff(m, bm);
+    sum_t acc = s * expd<MIX>(m, bm);
 #pragma unroll
     for (int q = 0; q < U; ++q)
-      acc += (expdiff(x[q][0], bm) + expdiff(x[q][1], bm)) +
-             (expdiff(x[q][2], bm) + expdiff(x[q][3], bm));
+      acc += (expd<MIX>(x[q][0], bm) + expd<MIX>(x[q][1], bm)) +
+             (expd<MIX>(x[q][2], bm) + expd<MIX>(x[q][3], bm));
     s = acc;
     m = bm;
   }
   // warp combine of (m, s)
   pot_t wm = warp_max(m);
-  sum_t ws = warp_sum(s * expdiff(m, wm));
+  sum_t ws = warp_sum(s * expd<MIX>(m, wm));
   return lse_fin(wm, ws);
 }
 
 // ---- the solver body ---------------------------------------------------------------------------
-template <bool P, bool VEC, int KG>
+template <bool P, bool VEC, int KG, bool MIX>
 __device__ void sinkhorn_run(const SkParams& p, unsigned char* smem_raw) {
   using pot_t = typename Tr<P>::pot_t;
   using sum_t = typename Tr<P>::sum_t;
@@ -140,8 +142,8 @@ __device__ void sinkhorn_run(const SkParams& p, unsigned char* smem_raw) {
             if (do_row) {
               const float* row = p.M + (int64_t)(r0 + warp) * p.ldm;
               pot_t lse;
-              if (p.v_in_smem) lse = row_lse<P, VEC, true>(row, vsrc, n1, ng, xf, lane);
-              else lse = row_lse<P, VEC, false>(row, vsrc, n1, ng, xf, lane);
+              if (p.v_in_smem) lse = row_lse<P, VEC, true, MIX>(row, vsrc, n1, ng, xf, lane);
+              else lse = row_lse<P, VEC, false, MIX>(row, vsrc, n1, ng, xf, lane);
               uval = loga - lse;
               if (lane == 0) {
                 u_work[r0 + warp] = uval;
@@ -181,9 +183,9 @@ __device__ void sinkhorn_run(const SkParams& p, unsigned char* smem_raw) {
                 x[q] = xf(cv, u_chunk[(rb + q) & (kSkChunk - 1)]);
                 bm = vmax(bm, x[q]);
               }
-              sum_t acc = cs[k][cc] * expdiff(cm[k][cc], bm);
+              sum_t acc = cs[k][cc] * expd<MIX>(cm[k][cc], bm);
 #pragma unroll
-              for (int q = 0; q < 8; ++q) acc += expdiff(x[q], bm);
+              for (int q = 0; q < 8; ++q) acc += expd<MIX>(x[q], bm);
               cs[k][cc] = acc;
               cm[k][cc] = bm;
             }
@@ -231,9 +233,9 @@ __device__ void sinkhorn_run(const SkParams& p, unsigned char* smem_raw) {
           }
           pot_t bm = vmax(vmax(mm[0], mm[1]), vmax(mm[2], mm[3]));
           bm = vmax(bm, m);
-          sum_t acc = s * expdiff(m, bm);
+          sum_t acc = s * expd<MIX>(m, bm);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) acc += ss[q] * expdiff(mm[q], bm);
+          for (int q = 0; q < 4; ++q) acc += ss[q] * expd<MIX>(mm[q], bm);
           s = acc; m = bm;
         }
       }
@@ -241,7 +243,7 @@ __device__ void sinkhorn_run(const SkParams& p, unsigned char* smem_raw) {
       pot_t gm = m;
 #pragma unroll
       for (int o = 4; o > 0; o >>= 1) gm = vmax(gm, __shfl_xor_sync(0xffffffffu, gm, o));
-      sum_t gs = s * expdiff(m, gm);
+      sum_t gs = s * expd<MIX>(m, gm);
 #pragma unroll
       for (int o = 4; o > 0; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
       if (act && sub == 0) {
@@ -311,7 +313,7 @@ __device__ void sinkhorn_run(const SkParams& p, unsigned char* smem_raw) {
     if (!(err == err)) flags |= CFM_FLAG_NONFINITE;
     p.status[0] = flags;
     p.status[1] = iters;
-    p.status[2] = P ? 1 : 0;
+    p.status[2] = P ? (MIX ? 2 : 1) : 0;  // 0 fp32, 1 float64, 2 float64 arguments + fp32 exponentials
     p.status[3] = 0;
     *p.err_out = err;
   }
@@ -327,8 +329,12 @@ __global__ void __launch_bounds__(kSkThreads, 1) sinkhorn_kernel(const SkParams 
     precise = !(span <= 64.f);
   }
   if (p.run_if == 2 && !precise) return;  // the fast case was taken by sinkhorn_v2_kernel
-  if (precise) sinkhorn_run<true, VEC, KG>(p, sk_smem);
-  else sinkhorn_run<false, VEC, KG>(p, sk_smem);
+  if (precise) {
+    if (p.mixed) sinkhorn_run<true, VEC, KG, true>(p, sk_smem);
+    else sinkhorn_run<true, VEC, KG, false>(p, sk_smem);
+  } else {
+    sinkhorn_run<false, VEC, KG, false>(p, sk_smem);
+  }
 }
 
 // ---- plan materialisation: plan_ij = exp(-M_ij/reg + log_u_i + log_v_j) in float64 ----------
@@ -436,6 +442,11 @@ extern "C" int cfm_sinkhorn_log_f32(const float* M, int n0, int n1, int64_t ldm,
     p.u_work = w + L.u; p.v_work[0] = w + L.v0; p.v_work[1] = w + L.v1;
     p.part_m = w + L.pm; p.part_s = w + L.ps; p.err_ring = reinterpret_cast<double*>(w + L.ring);
   }
+  // precise: -1 auto, 0 fp32, 1 float64, 2 fp32 on the generic kernel, 3 float64 with fp32 exponentials ("mixed")
+  static int auto_mixed = -1;  // CFM_SK_MIXED: what auto mode uses when it needs float64 potentials
+  if (auto_mixed < 0) { const char* e = getenv("CFM_SK_MIXED"); auto_mixed = e ? atoi(e) : 0; }
+  if (precise == 3) { precise = 1; p.precise = 1; p.mixed = 1; }
+  else if (precise < 0) p.mixed = auto_mixed;
   // fast fp32 mode on aligned n1 <= 8192: smem-staged kernel (sinkhorn_v2.cu)
   if (precise == 2) { precise = 0; p.precise = 0; }  // fast arithmetic, generic kernel (cross-checks)
   else if (precise != 1) {

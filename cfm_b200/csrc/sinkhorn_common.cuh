@@ -43,6 +43,7 @@ struct SkParams {
   float l2_resident_frac;  // sinkhorn_v2: share of each slab loaded with L2 evict_last (0: default policy)
   int dbg_flags;    // sinkhorn_v2 A/B switches (CFM_SK_DBG)
   int run_if;       // 0 always; 1 only when auto-mode resolves to fast; 2 only when it resolves to precise
+  int mixed;        // precise mode only: float64 potentials and exponent ARGUMENTS, fp32 exponentials (see expd)
 };
 
 template <bool P> struct Tr;
@@ -73,6 +74,15 @@ template <> struct Xf<true> {  // natural-log units, NumPy's fp32 rounding of -M
 };
 __device__ __forceinline__ float expdiff(float x, float m) { return ex2f(x - m); }
 __device__ __forceinline__ double expdiff(double x, double m) { return exp(x - m); }
+// exp(x - m) for the log-sum-exp recurrences.  MIX (float64 mode only): the difference is formed in float64 --
+// that is where |M/reg| ~ 1e4 needs the bits -- and only then rounded to fp32 and exponentiated with ex2:
+// relative error ~1e-7 per term instead of 1e-16, at a fifth of the float64-pipe instructions (a float64 exp is
+// ~30 of them, and this part issues one float64 warp instruction per ~16 cycles per scheduler).
+template <bool MIX> __device__ __forceinline__ float expd(float x, float m) { return ex2f(x - m); }
+template <bool MIX> __device__ __forceinline__ double expd(double x, double m) {
+  if (MIX) return (double)ex2f((float)(x - m) * kLog2e);
+  return exp(x - m);
+}
 __device__ __forceinline__ float lse_fin(float m, float s) { return m + log2f(s); }
 __device__ __forceinline__ double lse_fin(double m, double s) { return m + log(s); }
 __device__ __forceinline__ float vmax(float a, float b) { return fmaxf(a, b); }

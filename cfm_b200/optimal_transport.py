@@ -85,7 +85,8 @@ class OTPlanSampler:
     extras (not in the reference) tune the device solver:
 
     num_iter_max, stop_thr : POT's ``numItermax`` / ``stopThr`` for Sinkhorn (defaults 1000, 1e-9).
-    precision : 'auto' | 'fp32' | 'fp64' exponent arithmetic of the Sinkhorn kernel.
+    precision : 'auto' | 'fp32' | 'fp64' | 'fp64-mixed' exponent arithmetic of the Sinkhorn kernel
+        ('fp64-mixed': float64 potentials and exponent arguments, fp32 exponentials).
     stall_tol : stop once an fp32 fixed point is reached (see include/cfm_b200.h); 0 disables.
     cost_algo : 0 auto, 1 SIMT fp32, 2 tcgen05 3xTF32.
     """
@@ -121,7 +122,7 @@ class OTPlanSampler:
         self.warn = warn
         self.num_iter_max = int(num_iter_max)
         self.stop_thr = float(stop_thr)
-        if precision not in ("auto", "fp32", "fp64", "fp32-generic"):
+        if precision not in ("auto", "fp32", "fp64", "fp32-generic", "fp64-mixed"):
             raise ValueError(f"Unknown precision: {precision}")
         self.precision = precision
         self.stall_tol = float(stall_tol)
@@ -168,7 +169,7 @@ class OTPlanSampler:
         cp.status = torch.zeros(4, dtype=torch.int32, device=dev)
         cp.err = torch.zeros(1, dtype=torch.float64, device=dev)
         ws = _ffi.workspace(L.cfm_sinkhorn_workspace_bytes(n0, n1), dev)
-        prec = {"auto": -1, "fp32": 0, "fp64": 1, "fp32-generic": 2}[self.precision]
+        prec = {"auto": -1, "fp32": 0, "fp64": 1, "fp32-generic": 2, "fp64-mixed": 3}[self.precision]
         _ffi.check(L.cfm_sinkhorn_log_f32(
             _ffi.ptr(Mbuf), n0, n1, Mbuf.stride(0), float(reg), _ffi.ptr(cmax), int(bool(normalize)),
             int(self.num_iter_max if num_iter_max is None else num_iter_max),
@@ -253,7 +254,7 @@ class OTPlanSampler:
     def _report(self, cp):
         """Numerical guards of get_map (:88-96) + POT's non-convergence warning; one sync."""
         st = cp.status.cpu().tolist()
-        info = {"flags": st[0], "iterations": st[1], "precise": bool(st[2]), "method": cp.method}
+        info = {"flags": st[0], "iterations": st[1], "precise": bool(st[2]), "arithmetic": ("fp32", "fp64", "fp64-mixed")[st[2]] if 0 <= st[2] <= 2 else st[2], "method": cp.method}
         if cp.err is not None:
             info["err"] = float(cp.err.item())
         self.last_info = info

@@ -71,14 +71,16 @@ int cfm_tc_debug_buffer(unsigned long long* buf);
  * iterations (POT: 10) the column-marginal L2 error is tested against stop_thr.
  * precise: 0 = fp32 exponent arithmetic (|M/reg| <~ 64), 1 = float64 potentials and
  * IEEE fp32 division for -M/reg exactly as NumPy forms it, -1 = choose on device from
- * *cost_max / reg, 2 = fp32 arithmetic forced onto the generic (L2-reuse) kernel.
+ * *cost_max / reg, 2 = fp32 arithmetic forced onto the generic (L2-reuse) kernel, 3 = float64
+ * potentials and exponent arguments with fp32 exponentials (terms good to ~1e-7; five times fewer
+ * float64-pipe instructions than mode 1).
  * Outputs: log_u (n0), log_v (n1) float64 natural-log potentials with
  *   plan_ij = exp(-M_ij/reg + log_u_i + log_v_j);
  * stall_tol: 0 = POT's stopping rule only.  > 0 additionally stops at a check when the
  * error improved by less than this fraction since the previous check AND the RMS
  * relative column-marginal error is already < 1e-5 (fp32 fixed point reached; POT's
  * float64 loop would keep shaving an error our fp32 exponents cannot resolve).
- * status: int32[4] = {flags, iterations run, precise mode used, 0};
+ * status: int32[4] = {flags, iterations run, arithmetic used (0 fp32, 1 float64, 2 mode 3), kernel variant};
  * err: float64[1] last evaluated column-marginal L2 error.
  */
 size_t cfm_sinkhorn_workspace_bytes(int n0, int n1);
