@@ -21,6 +21,12 @@
 //     communication is ONE deterministic all-reduce (per-CTA partials -> grid barrier -> every CTA
 //     folds the partials in the same order) per step;
 //   * solver = euler needs no barrier at all.
+//
+// Tried and dropped (same 2.1-2.2 ms per C1 trajectory, so the simpler form stays): one row per warp with twice
+// the warps (shared-memory bandwidth-bound: every warp streams all 32 KB of hidden weights per evaluation), and
+// a K-split variant in which four warps share a row pair (a quarter of every layer's inputs each, partial sums
+// met behind 128-thread named barriers: 5x fewer instructions per warp, but four barriers per evaluation and the
+// Runge-Kutta arithmetic of a 2-D state serialised in one warp ate the gain).
 #include <cooperative_groups.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -524,413 +530,10 @@ __global__ void __launch_bounds__(MAXT, 1) ode_small_kernel(const OdeSmallParams
   }
 }
 
-// =====================================================================================================
-// K-split variant (the default): four warps share one row pair.
-//
-// ode_small_kernel above runs an evaluation entirely inside one warp: ~1600 instructions per evaluation on the
-// critical path, and a lone warp retires one instruction per 4-5 cycles (ncu: issue slots 24 % busy, 4300 cycles
-// per evaluation).  Here a GROUP of four warps evaluates the field for its row pair together: warp kq owns the
-// quarter [kq W/4, (kq+1) W/4) of every hidden layer's INPUTS.  For each hidden layer it forms the partial sums
-// of all W units over its inputs (weights from shared memory, 2 units x 2 rows per lane as before), the four
-// partials meet in shared memory behind one 128-thread named barrier, and warp kq then finalises (bias,
-// activation) exactly the units that are its own inputs of the next layer -- so the activations a warp consumes
-// never leave it.  Per evaluation a warp executes ~320 instructions and the group passes 4 named barriers.
-// The Runge-Kutta arithmetic is spread over the group's 128 threads by element; an element's k1..k7, x and
-// xnew are always touched by the same thread.
-constexpr int KQ = 4;
-
-struct GroupPlan {
-  int dimp, wq;
-  size_t wt0, wtime, b0, wt1, b1, wt2, b2, wt3, b3, grp, grp_stride, red, total;
-  // inside a group block (float offsets): xin, hloc, partA, partB, p3, state
-  size_t g_xin, g_hloc, g_pa, g_pb, g_p3, g_state;
-};
-__host__ __device__ inline GroupPlan ode_group_plan(int dim, int w, int ngroups, int pairs_per_group) {
-  GroupPlan s;
-  s.dimp = (dim + 3) / 4 * 4;
-  s.wq = w / KQ;
-  size_t o = 0;
-  auto take = [&](size_t n) { size_t r = o; o += (n + 3) / 4 * 4; return r; };
-  s.wt0 = take((size_t)dim * w); s.wtime = take(w); s.b0 = take(w);
-  s.wt1 = take((size_t)w * w); s.b1 = take(w);
-  s.wt2 = take((size_t)w * w); s.b2 = take(w);
-  s.wt3 = take((size_t)w * dim); s.b3 = take(dim);
-  size_t g = 0;
-  auto gtake = [&](size_t n) { size_t r = g; g += (n + 3) / 4 * 4; return r; };
-  s.g_xin = gtake((size_t)RB * s.dimp);
-  s.g_hloc = gtake((size_t)KQ * RB * s.wq);
-  s.g_pa = gtake((size_t)KQ * RB * w);
-  s.g_pb = gtake((size_t)KQ * RB * w);
-  s.g_p3 = gtake((size_t)KQ * RB * s.dimp);
-  s.g_state = gtake((size_t)pairs_per_group * RB * kSlots * s.dimp);
-  s.grp_stride = g;
-  s.grp = take((size_t)ngroups * g);
-  s.red = take(2 * 3 * 32 + 8);
-  s.total = o * sizeof(float);
-  return s;
-}
-
-__device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
-
-// One field evaluation for the group's row pair.  xin0 / xin1: the two input rows (dim floats, shared memory);
-// the result lands in out0 / out1 for the elements this thread owns (o = gtid, gtid + 128, ... over RB * dim;
-// row = o / dim) -- the caller's Runge-Kutta arithmetic uses the same ownership, so no barrier follows.
-template <int U>
-__device__ __noinline__ void group_eval(const float* __restrict__ sm, const GroupPlan& pl, int dim, int tv, int act,
-                                        const float* xin0, const float* xin1, float t, float* gbase, float* out0,
-                                        float* out1, int kq, int lane, int gtid, int barid) {
-  constexpr int W = 32 * U, WQ = W / KQ;
-  float* hloc = gbase + pl.g_hloc + (size_t)kq * RB * WQ;  // [RB][WQ], private to this warp
-  // layer 0: this warp's WQ units, both rows
-  for (int idx = lane; idx < RB * WQ; idx += 32) {
-    const int ul = idx % WQ, r = idx / WQ, unit = kq * WQ + ul;
-    const float* xr = r == 0 ? xin0 : xin1;
-    float a = sm[pl.b0 + unit];
-    if (tv) a = fmaf(t, sm[pl.wtime + unit], a);
-    for (int i = 0; i < dim; ++i) a = fmaf(sm[pl.wt0 + (size_t)i * W + unit], xr[i], a);
-    hloc[r * WQ + ul] = act_apply_fast(a, act);
-  }
-  __syncwarp();
-  const int u0 = U * lane;
-#pragma unroll 1
-  for (int layer = 0; layer < 2; ++layer) {
-    const float* wt = sm + (layer == 0 ? pl.wt1 : pl.wt2) + (size_t)kq * WQ * W;
-    const float* bb = sm + (layer == 0 ? pl.b1 : pl.b2);
-    float* part = gbase + (layer == 0 ? pl.g_pa : pl.g_pb);
-    float acc[RB][U], wv[U];
-#pragma unroll
-    for (int r = 0; r < RB; ++r)
-#pragma unroll
-      for (int q = 0; q < U; ++q) acc[r][q] = 0.f;
-#pragma unroll 2
-    for (int il = 0; il < WQ; il += 4) {
-      const float4 ha = *reinterpret_cast<const float4*>(hloc + il);
-      const float4 hb = *reinterpret_cast<const float4*>(hloc + WQ + il);
-      const float hs[RB][4] = {{ha.x, ha.y, ha.z, ha.w}, {hb.x, hb.y, hb.z, hb.w}};
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        lds_units<U>(wt + (size_t)(il + c) * W + u0, wv);
-#pragma unroll
-        for (int q = 0; q < U; ++q) {
-          acc[0][q] = fmaf(wv[q], hs[0][c], acc[0][q]);
-          acc[1][q] = fmaf(wv[q], hs[1][c], acc[1][q]);
-        }
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < RB; ++r) sts_units<U>(part + (size_t)(kq * RB + r) * W + u0, acc[r]);
-    group_bar(barid);
-    // finalise the units that are this warp's inputs of the next layer (fixed summation order: deterministic)
-    for (int idx = lane; idx < RB * WQ; idx += 32) {
-      const int ul = idx % WQ, r = idx / WQ, unit = kq * WQ + ul;
-      float a = bb[unit];
-#pragma unroll
-      for (int q = 0; q < KQ; ++q) a += part[(size_t)(q * RB + r) * W + unit];
-      hloc[r * WQ + ul] = act_apply_fast(a, act);
-    }
-    __syncwarp();
-  }
-  // layer 3: partial dot products over this warp's WQ hidden units, one lane per (row, output element)
-  float* p3 = gbase + pl.g_p3;
-  for (int o = lane; o < RB * dim; o += 32) {
-    const int r = o / dim, e = o - r * dim;
-    float a = 0.f;
-#pragma unroll 4
-    for (int ul = 0; ul < WQ; ++ul) a = fmaf(sm[pl.wt3 + (size_t)(kq * WQ + ul) * dim + e], hloc[r * WQ + ul], a);
-    p3[(size_t)(kq * RB + r) * pl.dimp + e] = a;
-  }
-  group_bar(barid);
-  for (int o = gtid; o < RB * dim; o += 128) {
-    const int r = o / dim, e = o - r * dim;
-    float a = sm[pl.b3 + e];
-#pragma unroll
-    for (int q = 0; q < KQ; ++q) a += p3[(size_t)(q * RB + r) * pl.dimp + e];
-    (r == 0 ? out0 : out1)[e] = a;
-  }
-}
-
-template <int U, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) ode_group_kernel(const OdeSmallParams p) {
-  constexpr int W = 32 * U;
-  extern __shared__ __align__(16) float sm[];
-  cg::grid_group grid = cg::this_grid();
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  const int ngroups = nwarps / KQ, g = warp / KQ, kq = warp % KQ, gtid = tid & 127, barid = 1 + g;
-  const int dim = p.dim, tv = p.tv, act = p.act, ppg = p.rows_per_warp;  // here: row PAIRS per group
-  const GroupPlan pl = ode_group_plan(dim, W, ngroups, ppg);
-  const int dimp = pl.dimp;
-  const int in0 = dim + tv;
-
-  for (int idx = tid; idx < W * dim; idx += blockDim.x) {
-    const int u = idx / dim, i = idx % dim;
-    sm[pl.wt0 + (size_t)i * W + u] = p.W0[(size_t)u * in0 + i];
-  }
-  for (int u = tid; u < W; u += blockDim.x) {
-    sm[pl.wtime + u] = tv ? p.W0[(size_t)u * in0 + dim] : 0.f;
-    sm[pl.b0 + u] = p.b0[u];
-    sm[pl.b1 + u] = p.b1[u];
-    sm[pl.b2 + u] = p.b2[u];
-  }
-  for (int idx = tid; idx < W * W; idx += blockDim.x) {
-    const int u = idx / W, i = idx % W;
-    sm[pl.wt1 + (size_t)i * W + u] = p.W1[idx];
-    sm[pl.wt2 + (size_t)i * W + u] = p.W2[idx];
-  }
-  for (int idx = tid; idx < dim * W; idx += blockDim.x) {
-    const int e = idx / W, i = idx % W;
-    sm[pl.wt3 + (size_t)i * dim + e] = p.W3[idx];
-  }
-  for (int e = tid; e < dim; e += blockDim.x) sm[pl.b3 + e] = p.b3[e];
-
-  float* gbase = sm + pl.grp + (size_t)g * pl.grp_stride;
-  float* xin = gbase + pl.g_xin;  // [RB][dimp]
-  double* red = reinterpret_cast<double*>(sm + pl.red);
-  const int64_t ggroup = (int64_t)blockIdx.x * ngroups + g, gstride = (int64_t)gridDim.x * ngroups;
-  const int64_t B = p.B;
-  // row of (pair q of this group, member m); state slot s of that row
-  auto row_of = [&](int q, int m) -> int64_t { return (ggroup + (int64_t)q * gstride) * RB + m; };
-  auto slot = [&](int q, int m, int s_) -> float* {
-    return gbase + pl.g_state + (((size_t)q * RB + m) * kSlots + s_) * dimp;
-  };
-  const double numel = (double)B * (double)dim;
-  const int nel = RB * dim;  // elements of a row pair; element o -> (member o / dim, component o % dim)
-
-  for (int q = 0; q < ppg; ++q)
-    for (int o = gtid; o < nel; o += 128) {
-      const int m = o / dim, e = o - m * dim;
-      const int64_t r = row_of(q, m);
-      const float v = r < B ? p.x0[r * dim + e] : 0.f;
-      slot(q, m, 0)[e] = v;
-      if (r < B) p.traj[r * dim + e] = v;
-    }
-  __syncthreads();
-
-  const int n_span = p.n_span;
-  if (p.solver == 1) {
-    for (int n = 0; n + 1 < n_span; ++n) {
-      const float t = __ldg(p.t_span + n), h = __ldg(p.t_span + n + 1) - t;
-      for (int q = 0; q < ppg; ++q) {
-        if (row_of(q, 0) >= B) break;
-        group_eval<U>(sm, pl, dim, tv, act, slot(q, 0, 0), slot(q, 1, 0), t, gbase, slot(q, 0, 1), slot(q, 1, 1), kq,
-                      lane, gtid, barid);
-        for (int o = gtid; o < nel; o += 128) {
-          const int m = o / dim, e = o - m * dim;
-          const int64_t r = row_of(q, m);
-          const float v = fmaf(h, slot(q, m, 1)[e], slot(q, m, 0)[e]);
-          slot(q, m, 0)[e] = v;
-          if (r < B) p.traj[((int64_t)(n + 1) * B + r) * dim + e] = v;
-        }
-        group_bar(barid);  // the new x is read by all four warps in the next evaluation
-      }
-    }
-    if (blockIdx.x == 0 && tid == 0) {
-      cfm_rk_state* st = p.st;
-      st->t = __ldg(p.t_span + n_span - 1);
-      st->done = 1;
-      st->nfe = n_span - 1;
-      st->accepted = n_span - 1;
-      st->rejected = 0;
-    }
-    return;
-  }
-
-  const float atol = p.atol, rtol = p.rtol;
-  float t = __ldg(p.t_span), dt = 0.f, dt_old = 0.f, ratio = 0.f;
-  const float t_end = __ldg(p.t_span + n_span - 1);
-  int ckpt = 1, ckpt_flag = 0, done = 0, accepted = 0, rejected = 0, nfe = 0, pbuf = 0;
-  auto prestep = [&]() {
-    if (!(t < t_end)) { done = 1; return; }
-    if (t + dt > t_end) dt = t_end - t;
-    if (ckpt < n_span && t + dt > __ldg(p.t_span + ckpt)) {
-      dt_old = dt;
-      ckpt_flag = 1;
-      dt = __ldg(p.t_span + ckpt) - t;
-    }
-  };
-
-  {
-    double s2[2] = {0.0, 0.0};
-    for (int q = 0; q < ppg; ++q) {
-      if (row_of(q, 0) >= B) break;
-      group_eval<U>(sm, pl, dim, tv, act, slot(q, 0, 0), slot(q, 1, 0), t, gbase, slot(q, 0, 1), slot(q, 1, 1), kq,
-                    lane, gtid, barid);
-      for (int o = gtid; o < nel; o += 128) {
-        const int m = o / dim, e = o - m * dim;
-        if (row_of(q, m) >= B) continue;
-        const float xv = slot(q, m, 0)[e], f0 = slot(q, m, 1)[e];
-        const float sc = atol + fabsf(xv) * rtol;
-        const float a = xv / sc, b = f0 / sc;
-        s2[0] += (double)a * a;
-        s2[1] += (double)b * b;
-      }
-    }
-    grid_sum<2>(grid, s2, p.partials, pbuf, red);
-    pbuf ^= 1;
-    const float d0 = (float)sqrt(s2[0] / numel), d1 = (float)sqrt(s2[1] / numel);
-    const float h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : 0.01f * d0 / d1;
-    double s1[1] = {0.0};
-    for (int q = 0; q < ppg; ++q) {
-      if (row_of(q, 0) >= B) break;
-      for (int o = gtid; o < nel; o += 128) {
-        const int m = o / dim, e = o - m * dim;
-        xin[m * dimp + e] = fmaf(h0, slot(q, m, 1)[e], slot(q, m, 0)[e]);
-      }
-      group_bar(barid);
-      group_eval<U>(sm, pl, dim, tv, act, xin, xin + dimp, t + h0, gbase, slot(q, 0, 2), slot(q, 1, 2), kq, lane, gtid,
-                    barid);
-      for (int o = gtid; o < nel; o += 128) {
-        const int m = o / dim, e = o - m * dim;
-        if (row_of(q, m) >= B) continue;
-        const float sc = atol + fabsf(slot(q, m, 0)[e]) * rtol;
-        const float dq = (slot(q, m, 2)[e] - slot(q, m, 1)[e]) / sc;
-        s1[0] += (double)dq * dq;
-      }
-      group_bar(barid);  // xin is rewritten for the next pair
-    }
-    grid_sum<1>(grid, s1, p.partials, pbuf, red);
-    pbuf ^= 1;
-    const float d2 = (float)sqrt(s1[0] / numel) / h0;
-    float h1;
-    if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, h0 * 1e-3f);
-    else h1 = powf(0.01f / fmaxf(d1, d2), 1.f / 6.f);
-    dt = fminf(100.f * h0, h1);
-    dt_old = h0;
-    nfe = 2;
-    prestep();
-  }
-
-  int steps = 0;
-  long long c_eval = 0, c_sum = 0, c_ctl = 0;
-  const long long c_begin = clock64();
-  while (!done && steps < p.max_steps) {
-    ++steps;
-    long long c0 = clock64();
-    double es[1] = {0.0};
-    for (int q = 0; q < ppg; ++q) {
-      if (row_of(q, 0) >= B) break;
-#pragma unroll 1
-      for (int stage = 1; stage <= 6; ++stage) {
-        float a[6];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) a[j] = dt * oA[stage][j];
-        float* d0p = stage < 6 ? xin : slot(q, 0, 8);
-        float* d1p = stage < 6 ? xin + dimp : slot(q, 1, 8);
-        for (int o = gtid; o < nel; o += 128) {
-          const int m = o / dim, e = o - m * dim;
-          float v = slot(q, m, 0)[e];
-#pragma unroll
-          for (int j = 0; j < 6; ++j)
-            if (j < stage && oA[stage][j] != 0.f) v = fmaf(a[j], slot(q, m, 1 + j)[e], v);
-          (m == 0 ? d0p : d1p)[e] = v;
-        }
-        group_bar(barid);
-        group_eval<U>(sm, pl, dim, tv, act, d0p, d1p, t + oC[stage] * dt, gbase, slot(q, 0, 1 + stage),
-                      slot(q, 1, 1 + stage), kq, lane, gtid, barid);
-      }
-      for (int o = gtid; o < nel; o += 128) {
-        const int m = o / dim, e = o - m * dim;
-        if (row_of(q, m) >= B) continue;
-        float er = 0.f;
-#pragma unroll
-        for (int j = 0; j < 7; ++j)
-          if (oE[j] != 0.f) er = fmaf(oE[j], slot(q, m, 1 + j)[e], er);
-        er *= dt;
-        const float tol = atol + rtol * fmaxf(fabsf(slot(q, m, 0)[e]), fabsf(slot(q, m, 8)[e]));
-        const float rr = er / tol;
-        es[0] += (double)rr * (double)rr;
-      }
-      group_bar(barid);  // xin / the state of this pair is rewritten by the next pair's / next step's stage 1
-    }
-    long long c1 = clock64();
-    c_eval += c1 - c0;
-    grid_sum<1>(grid, es, p.partials, pbuf, red);
-    pbuf ^= 1;
-    c0 = clock64();
-    c_sum += c0 - c1;
-    ratio = (float)sqrt(es[0] / numel);
-    nfe += 6;
-    const bool accept = ratio <= 1.f;
-    int save_slot = -1;
-    if (accept) {
-      float tn = t + dt;
-      if (ckpt < n_span && (tn == __ldg(p.t_span + ckpt) || ckpt_flag)) {
-        tn = __ldg(p.t_span + ckpt);
-        save_slot = ckpt;
-        ckpt++;
-      }
-      t = tn;
-      accepted++;
-    } else {
-      rejected++;
-    }
-    float ndt = dt;
-    if (ckpt_flag) { ndt = dt_old - dt; ckpt_flag = 0; }
-    if (ratio == 0.f) {
-      ndt = ndt * 10.f;
-    } else {
-      const float min_factor = ratio < 1.f ? 1.f : 0.2f;
-      const float factor = fminf(10.f, fmaxf(0.9f / powf(ratio, 0.2f), min_factor));
-      ndt = ndt * factor;
-    }
-    dt = ndt;
-    prestep();
-    if (accept) {
-      for (int q = 0; q < ppg; ++q) {
-        if (row_of(q, 0) >= B) break;
-        for (int o = gtid; o < nel; o += 128) {
-          const int m = o / dim, e = o - m * dim;
-          const int64_t r = row_of(q, m);
-          const float v = slot(q, m, 8)[e];
-          slot(q, m, 0)[e] = v;
-          slot(q, m, 1)[e] = slot(q, m, 7)[e];
-          if (save_slot >= 0 && r < B) p.traj[((int64_t)save_slot * B + r) * dim + e] = v;
-        }
-      }
-    }
-    c_ctl += clock64() - c0;
-  }
-  if (p.dbg && blockIdx.x == 0 && tid == 0)
-    printf("ode_group: steps %d  cycles total %lld  stages+evals %lld  grid_sum %lld  control+commit %lld\n", steps,
-           clock64() - c_begin, c_eval, c_sum, c_ctl);
-  if (blockIdx.x == 0 && tid == 0) {
-    cfm_rk_state* st = p.st;
-    st->t = t; st->dt = dt; st->t_end = t_end; st->atol = atol; st->rtol = rtol;
-    st->dt_old = dt_old; st->ratio = ratio; st->ckpt_flag = ckpt_flag; st->ckpt = ckpt;
-    st->n_span = n_span; st->commit = 0; st->done = done; st->save_slot = -1;
-    st->accepted = accepted; st->rejected = rejected; st->nfe = nfe; st->err_acc = 0.0;
-  }
-}
-
 struct Launch {
-  int grid, nwarps, rpw;  // rpw: rows per warp (warp kernel) / row pairs per group (group kernel)
+  int grid, nwarps, rpw;
   size_t smem;
-  int group;              // 1: ode_group_kernel, 0: ode_small_kernel
 };
-
-static int use_group_kernel() {
-  static int v = -1;  // CFM_ODE_VARIANT=group / warp selects the kernel (A/B, tests); default below
-  if (v < 0) { const char* e = getenv("CFM_ODE_VARIANT"); v = e ? (e[0] == 'g' ? 1 : 0) : 0; }
-  return v;
-}
-
-template <int U>
-int plan_group(int64_t B, int dim, Launch* out) {
-  const int sms = sm_count();
-  const int64_t pairs = (B + RB - 1) / RB;
-  for (int ngroups = 1; ngroups <= 8; ngroups *= 2) {
-    int64_t grid = (pairs + ngroups - 1) / ngroups;
-    if (grid > sms) grid = sms;
-    const int64_t per = grid * ngroups;
-    const int64_t ppg = (pairs + per - 1) / per;
-    if (ppg > 1 && ngroups < 8) continue;  // prefer more groups per CTA over several pairs per group
-    if (ppg > (1 << 19)) return 0;
-    const GroupPlan pl = ode_group_plan(dim, 32 * U, ngroups, (int)ppg);
-    if (pl.total > 200 * 1024) return 0;
-    out->grid = (int)grid; out->nwarps = ngroups * KQ; out->rpw = (int)ppg; out->smem = pl.total; out->group = 1;
-    return 1;
-  }
-  return 0;
-}
 
 template <int U>
 int plan_launch(int64_t B, int dim, Launch* out) {
@@ -945,7 +548,7 @@ int plan_launch(int64_t B, int dim, Launch* out) {
     if (gpw > (1 << 19)) return 0;
     const SmemPlan pl = ode_small_plan(dim, 32 * U, nwarps, (int)gpw * RB);
     if (pl.total > 200 * 1024) return 0;
-    out->grid = (int)grid; out->nwarps = nwarps; out->rpw = (int)gpw * RB; out->smem = pl.total; out->group = 0;
+    out->grid = (int)grid; out->nwarps = nwarps; out->rpw = (int)gpw * RB; out->smem = pl.total;
     return 1;
   }
   return 0;
@@ -953,11 +556,6 @@ int plan_launch(int64_t B, int dim, Launch* out) {
 
 int plan_any(int64_t B, int dim, int w, Launch* out) {
   if (B <= 0 || dim <= 0 || dim > 1024) return 0;
-  if (use_group_kernel()) {
-    if (w == 32 && plan_group<1>(B, dim, out)) return 1;
-    if (w == 64 && plan_group<2>(B, dim, out)) return 1;
-    if (w == 128 && plan_group<4>(B, dim, out)) return 1;
-  }
   if (w == 32) return plan_launch<1>(B, dim, out);
   if (w == 64) return plan_launch<2>(B, dim, out);
   if (w == 128) return plan_launch<4>(B, dim, out);
@@ -966,7 +564,7 @@ int plan_any(int64_t B, int dim, int w, Launch* out) {
 
 template <int U, int MAXT>
 int launch_t(const OdeSmallParams& p, const Launch& L, cudaStream_t s) {
-  const void* kern = L.group ? (const void*)ode_group_kernel<U, MAXT> : (const void*)ode_small_kernel<U, MAXT>;
+  const void* kern = (const void*)ode_small_kernel<U, MAXT>;
   CFM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
   int per_sm = 0;
   CFM_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, L.nwarps * 32, L.smem));

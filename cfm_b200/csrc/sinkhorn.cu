@@ -444,7 +444,7 @@ extern "C" int cfm_sinkhorn_log_f32(const float* M, int n0, int n1, int64_t ldm,
   }
   // precise: -1 auto, 0 fp32, 1 float64, 2 fp32 on the generic kernel, 3 float64 with fp32 exponentials ("mixed")
   static int auto_mixed = -1;  // CFM_SK_MIXED: what auto mode uses when it needs float64 potentials
-  if (auto_mixed < 0) { const char* e = getenv("CFM_SK_MIXED"); auto_mixed = e ? atoi(e) : 0; }
+  if (auto_mixed < 0) { const char* e = getenv("CFM_SK_MIXED"); auto_mixed = e ? atoi(e) : 1; }  // measured at C4 (N=4096, 100 it): 16.5 ms float64, 9.5 ms mixed, same err to 1e-9
   if (precise == 3) { precise = 1; p.precise = 1; p.mixed = 1; }
   else if (precise < 0) p.mixed = auto_mixed;
   // fast fp32 mode on aligned n1 <= 8192: smem-staged kernel (sinkhorn_v2.cu)

@@ -254,7 +254,12 @@ class OTPlanSampler:
     def _report(self, cp):
         """Numerical guards of get_map (:88-96) + POT's non-convergence warning; one sync."""
         st = cp.status.cpu().tolist()
-        info = {"flags": st[0], "iterations": st[1], "precise": bool(st[2]), "arithmetic": ("fp32", "fp64", "fp64-mixed")[st[2]] if 0 <= st[2] <= 2 else st[2], "method": cp.method}
+        if cp.method == "exact":  # status = {flags, augmentations, Dijkstra steps, -}
+            info = {"flags": st[0], "iterations": st[1], "dijkstra_steps": st[2], "precise": True, "method": cp.method}
+        else:                     # status = {flags, iterations, arithmetic, kernel variant}
+            info = {"flags": st[0], "iterations": st[1], "precise": bool(st[2]),
+                    "arithmetic": ("fp32", "fp64", "fp64-mixed")[st[2]] if 0 <= st[2] <= 2 else st[2],
+                    "method": cp.method}
         if cp.err is not None:
             info["err"] = float(cp.err.item())
         self.last_info = info
