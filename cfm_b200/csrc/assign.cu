@@ -46,6 +46,7 @@ struct AsgParams {
   int32_t* g_srlist;   // n
   unsigned char* g_sc; // n
   int use_smem;
+  int cache_rows;      // assign_fast_kernel: the first cache_rows rows of M are staged in shared memory
 };
 
 struct MinKey {
@@ -263,6 +264,18 @@ __global__ void __launch_bounds__(1024, 1) assign_fast_kernel(const AsgParams p)
   int32_t* c4r = path_s + n;                               // n   col4row
   int32_t* srlist = c4r + n;                               // n
   int32_t* r4c_s = srlist + n;                             // n   row4col
+  // The cost row of the current search row is THE long-latency operation of a Dijkstra step (ncu: the first use
+  // of the loaded cost is the top stall; M no longer fits the L1 next to everything else at n = 256).  The rows
+  // that fit are staged in shared memory once; the search reads them with LDS latency.
+  const float* mcache = reinterpret_cast<const float*>(r4c_s + n);
+  const int ncache = p.cache_rows;
+  {
+    float* mc = const_cast<float*>(mcache);
+    for (int idx = tid; idx < ncache * n; idx += nt) {
+      const int r = idx / n, j = idx - r * n;
+      mc[idx] = __ldg(p.M + (int64_t)r * p.ldm + j);
+    }
+  }
   __shared__ unsigned long long wk[2][32];
   __shared__ unsigned wsec[2][32];
   __shared__ double wsum[32];
@@ -353,10 +366,16 @@ __global__ void __launch_bounds__(1024, 1) assign_fast_kernel(const AsgParams p)
       if (tid == 0) srlist[nsr] = i;
       ++nsr;
       const double base = minval - u[i];
-      const float* mrow = p.M + (int64_t)i * p.ldm + tid;
       float c[KCB];
+      if (i < ncache) {
+        const float* mrow = mcache + (size_t)i * n + tid;
 #pragma unroll
-      for (int k = 0; k < KCB; ++k) c[k] = (padmask >> k) & 1u ? 0.f : __ldg(mrow + nt * k);
+        for (int k = 0; k < KCB; ++k) c[k] = (padmask >> k) & 1u ? 0.f : mrow[nt * k];
+      } else {
+        const float* mrow = p.M + (int64_t)i * p.ldm + tid;
+#pragma unroll
+        for (int k = 0; k < KCB; ++k) c[k] = (padmask >> k) & 1u ? 0.f : __ldg(mrow + nt * k);
+      }
       IKey best{~0ull, 0xffffffffu};
 #pragma unroll
       for (int k = 0; k < KCB; ++k) {
@@ -488,7 +507,14 @@ extern "C" int cfm_assign_exact_f32(const float* M, int n, int64_t ldm, const fl
   static int force_block = -1;  // CFM_ASSIGN_BLOCK=1: always use the block-wide kernel (A/B timing, tests)
   if (force_block < 0) { const char* e = getenv("CFM_ASSIGN_BLOCK"); force_block = e ? atoi(e) : 0; }
   if (n <= 4096 && !force_block) {
-    const size_t sb = asg_fast_smem_bytes(n);
+    size_t sb = asg_fast_smem_bytes(n);
+    {
+      const size_t room = (size_t)200 * 1024 > sb ? (size_t)200 * 1024 - sb : 0;
+      size_t rows = room / ((size_t)n * 4);
+      if (rows > (size_t)n) rows = n;
+      p.cache_rows = (int)rows;
+      sb += rows * (size_t)n * 4;
+    }
     int nt = ((n + 31) / 32) * 32;
     if (nt < 64) nt = 64;
     if (nt > 1024) nt = 1024;
