@@ -258,7 +258,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int quad = warp & 3;               // TMEM lane quadrant this warp may touch
     const int half = (warp - 2) >> 2;         // which half of the tile's columns this warp drains
     constexpr int kColsPerWarp = kTN / (kEpiWarps / 4);
