@@ -338,7 +338,7 @@ def main():
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("sinkhorn_kernel_dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "sinkhorn_kernel (100 fused sweeps, one launch)",
+    roofline = {"bound": "hbm", "kernel": "sinkhorn_v2_kernel<512,4,2> (100 fused sweeps, one cooperative launch)",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "peak_source": which,
                 "note": "algorithmic bytes = iters*2*N^2*4 (two passes per iteration); the fused sweep "
