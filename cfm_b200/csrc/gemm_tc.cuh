@@ -19,6 +19,8 @@
 // Users: sqdist_tc.cu (cost matrix), mlp_tc.cu (vector-field MLP layers).
 #pragma once
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -203,6 +205,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   if (threadIdx.x == 0) TC_MARK(1);  // barriers initialised, TMEM allocated
+  // Programmatic dependent launch: everything above touches no memory written by the preceding kernel, so when
+  // this grid is launched with the programmatic-serialization attribute its prologue overlaps the tail of its
+  // predecessor; from here on the predecessor's results are needed (operands via TMA, the device scalar t).
+  // Without the attribute both instructions are no-ops.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -329,7 +337,21 @@ inline int launch_gemm_tc(const float* ah, const float* al, int n0, int64_t lda,
   CFM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
   int grid = p.tiles_m * p.tiles_n;
   if (grid > sm_count()) grid = sm_count();
-  kern<<<grid, kTcThreads, kSmem, s>>>(mah, mal, mbh, mbl, p, epi); ::cfm::note_launches(1);
+  static int pdl = -1;  // CFM_TC_PDL=1: launch as a programmatic dependent of the preceding kernel in the stream
+  if (pdl < 0) { const char* e = getenv("CFM_TC_PDL"); pdl = e ? atoi(e) : 0; }
+  if (pdl) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = kSmem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CFM_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mah, mal, mbh, mbl, p, epi));
+  } else {
+    kern<<<grid, kTcThreads, kSmem, s>>>(mah, mal, mbh, mbl, p, epi);
+  }
+  ::cfm::note_launches(1);
   CFM_CUDA_OK(cudaGetLastError());
   return CFM_OK;
 }
