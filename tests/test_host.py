@@ -212,3 +212,51 @@ def test_sharded_pairs_gloo_world2(sizes):
     for rank, i, j, ig, jg in res:
         assert i == list(range(sizes[rank]))
         assert ig == want_i and jg == want_j
+
+
+# ---- property tests (hypothesis) of the pure-host pieces -----------------------------------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.integers(0, 100000), st.integers(1, 64))
+def test_shard_bounds_properties(n, ws):
+    cuts = [cdist.shard_bounds(n, ws, r) for r in range(ws)]
+    assert cuts[0][0] == 0 and cuts[-1][1] == n
+    assert all(lo <= hi for lo, hi in cuts)
+    assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+    sizes = [hi - lo for lo, hi in cuts]
+    assert max(sizes) - min(sizes) <= 1 and sum(sizes) == n
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(1, 9), st.lists(st.integers(1, 4), min_size=0, max_size=3), st.floats(0.0, 2.0),
+       st.sampled_from(["i_cfm", "t_cfm", "vp_cfm"]), st.integers(0, 2**31 - 1))
+def test_non_ot_matchers_equal_the_oracle_formulas_on_any_shape(bs, dims, sigma, kind, seed):
+    """The CPU (autograd / non-fused) branch of the non-OT matchers against the oracle's restatement of the
+    reference formulas, bit for bit, for arbitrary trailing shapes (the fused CUDA branch is tested on the GPU)."""
+    from oracle import coupling as oc
+    cls = {"i_cfm": cfm_b200.ConditionalFlowMatcher, "t_cfm": cfm_b200.TargetConditionalFlowMatcher,
+           "vp_cfm": cfm_b200.VariancePreservingConditionalFlowMatcher}[kind]
+    g = torch.Generator().manual_seed(seed)
+    shape = (bs, *dims) if dims else (bs, 1)
+    x0, x1 = torch.randn(shape, generator=g), torch.randn(shape, generator=g)
+    t = torch.rand(bs, generator=g)
+    fm = cls(sigma=sigma)
+    torch.manual_seed(seed % 1000)
+    tt, xt, ut, eps = fm.sample_location_and_conditional_flow(x0, x1, t=t, return_noise=True)
+    want_xt, want_ut = oc.matcher_xt_ut(kind, x0, x1, t, eps, sigma)
+    assert torch.equal(tt, t) and torch.equal(xt, want_xt) and torch.equal(ut, want_ut)
+    lam = fm.compute_lambda(t)
+    assert torch.is_tensor(lam) or isinstance(lam, float)
+
+
+@settings(max_examples=50, deadline=None)
+@given(st.integers(1, 6), st.lists(st.integers(1, 5), min_size=0, max_size=4))
+def test_pad_t_like_x_broadcasts(bs, dims):
+    x = torch.zeros((bs, *dims))
+    t = torch.arange(bs, dtype=torch.float32)
+    p = cfm_b200.pad_t_like_x(t, x)
+    assert p.shape == (bs,) + (1,) * len(dims)
+    assert (p * torch.ones_like(x) if dims else p).shape == x.shape
+    assert cfm_b200.pad_t_like_x(0.5, x) == 0.5
