@@ -66,3 +66,30 @@ def sharded_sample_plan(sampler, x0_local, x1_local, group=None):
     the global index pairs.  Returns (x0_local[i], x1_local[j], i_global, j_global)."""
     i, j, ig, jg = sharded_sample_pairs(sampler, x0_local, x1_local, group=group, gather=True)
     return sampler._gather(x0_local, i), sampler._gather(x1_local, j), ig, jg
+
+
+def sharded_trajectory(node, x, t_span, group=None, gather=True, integrate_fn=None):
+    """ODE sampling across ranks ("MLP / ODE sampling"): rows are independent and the weights
+    are replicated, so rank r integrates its contiguous shard of ``x`` with its own step controller -- what a
+    data-parallel caller of torchdyn does, zero communication during the integration -- and, if ``gather``, one
+    all_gather returns the full (len(t_span), B, *dim) trajectory on every rank.
+
+    Per-shard controllers take the step sequence their own shard's error norm dictates (torchdyn's norm is a
+    mean over whatever batch it is given), so the result agrees with a single-process run to the solver
+    tolerance, not bit for bit.  ``integrate_fn`` (tests only) replaces ``node.trajectory``.
+    """
+    fn = integrate_fn if integrate_fn is not None else node.trajectory
+    if not dist.is_available() or not dist.is_initialized():
+        return fn(x, t_span)
+    ws, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = shard_bounds(x.shape[0], ws, rank)
+    local = fn(x[lo:hi], t_span)  # (T, hi - lo, *dim)
+    if not gather:
+        return local
+    sizes = [shard_bounds(x.shape[0], ws, r) for r in range(ws)]
+    pad = max(h - l for l, h in sizes)
+    buf = local.new_zeros((local.shape[0], pad) + tuple(local.shape[2:]))
+    buf[:, :hi - lo] = local
+    outs = [torch.empty_like(buf) for _ in range(ws)]
+    dist.all_gather(outs, buf.contiguous(), group=group)
+    return torch.cat([o[:, :h - l] for o, (l, h) in zip(outs, sizes)], dim=1)

@@ -260,3 +260,39 @@ def test_pad_t_like_x_broadcasts(bs, dims):
     assert p.shape == (bs,) + (1,) * len(dims)
     assert (p * torch.ones_like(x) if dims else p).shape == x.shape
     assert cfm_b200.pad_t_like_x(0.5, x) == 0.5
+
+
+def _gloo_traj_worker(rank, world, port, n, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        x = torch.arange(n * 2, dtype=torch.float32).reshape(n, 2)
+        span = torch.linspace(0, 1, 3)
+
+        def fake_integrate(xs, ts):  # row-wise, shard-independent stand-in for NeuralODE.trajectory
+            return torch.stack([xs * (1.0 + float(t)) for t in ts])
+
+        full = cdist.sharded_trajectory(None, x, span, integrate_fn=fake_integrate)
+        local = cdist.sharded_trajectory(None, x, span, gather=False, integrate_fn=fake_integrate)
+        q.put((rank, full.tolist(), list(local.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [8, 7])
+def test_sharded_trajectory_gloo_world2(n):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + n
+    procs = [ctx.Process(target=_gloo_traj_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    x = torch.arange(n * 2, dtype=torch.float32).reshape(n, 2)
+    want = torch.stack([x * (1.0 + float(t)) for t in torch.linspace(0, 1, 3)]).tolist()
+    for rank, full, lshape in res:
+        assert full == want
+        lo, hi = cdist.shard_bounds(n, 2, rank)
+        assert lshape == [3, hi - lo, 2]
