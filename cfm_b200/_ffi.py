@@ -50,7 +50,7 @@ SIGNATURES = {
     "cfm_plan_dot_cost": (_i, [_p, _i, _i, _i64, _f, _p, _i, _p, _p, _p, _p]),
     "cfm_plan_sample_workspace_bytes": (_sz, [_i]),
     "cfm_plan_sample": (_i, [_p, _i, _i, _i64, _f, _p, _i, _p, _p, _i, _p, _i, _p, _p, _p, _p, _sz, _p]),
-    "cfm_plan_sample_rows": (_i, [_p, _i, _i, _i64, _f, _p, _i, _p, _p, _p, _i, _p, _p, _p]),
+    "cfm_plan_sample_rows": (_i, [_p, _i, _i, _i64, _f, _p, _i, _p, _p, _p, _p, _i, _p, _p, _p]),
     "cfm_dense_plan_sample_f64": (_i, [_p, _i, _i, _p, _i, _p, _p, _p, _sz, _p]),
     "cfm_perm_plan_sample": (_i, [_p, _p, _i, _p, _i, _p, _p, _p]),
     "cfm_assign_workspace_bytes": (_sz, [_i]),
@@ -69,6 +69,9 @@ SIGNATURES = {
     "cfm_rk_commit": (_i, [_p, _p, _p, _p, _p, _i64, _p]),
     "cfm_rk_init_a": (_i, [_p, _p, _p, _p, _p, _p, _i64, _p]),
     "cfm_rk_init_b": (_i, [_p, _p, _p, _p, _p, _p, _i64, _p]),
+    "cfm_rk_init_sums": (_i, [_p, _p, _p, _p, _p, _i64, _i, _p]),
+    "cfm_rk_init_probe": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _p]),
+    "cfm_rk_init_finish": (_i, [_p, _p, _p, _i64, _p]),
     "cfm_axpy_f32": (_i, [_p, _p, _f, _p, _i64, _p]),
     "cfm_ode_small_supported": (_i, [_i64, _i, _i, _i]),
     "cfm_ode_small_workspace_bytes": (_sz, [_i64, _i, _i]),

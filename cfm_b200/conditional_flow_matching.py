@@ -85,7 +85,9 @@ class ConditionalFlowMatcher:
         """Common tail of every matcher: draw t and eps in the reference's order, then xt / ut either
         by the fused kernel (pairs given by device index tensors i, j or identity) or by torch ops."""
         n = x0.shape[0] if i is None else i.shape[0]
-        if not self._fused_ok(x0, x1):
+        # a caller-supplied t of another dtype (float64 ...) promotes xt / ut in the reference: torch-op path
+        t_ok = t is None or (torch.is_tensor(t) and t.dtype == x0.dtype)
+        if not (t_ok and self._fused_ok(x0, x1)):
             if i is not None:
                 x0, x1 = x0[i], x1[j]
             if t is None:
@@ -109,10 +111,11 @@ class ConditionalFlowMatcher:
         row = 1
         for dsz in shape[1:]:
             row *= dsz
-        _ffi.check(_ffi.lib().cfm_flow_pairs_f32(
-            self._FUSED_KIND, _ffi.ptr(x0c), _ffi.ptr(x1c), _ffi.ptr(i), _ffi.ptr(j), _ffi.ptr(eps),
-            _ffi.ptr(ra), _ffi.ptr(rb), _ffi.ptr(rs), _ffi.ptr(rc), sig, kon, _ffi.ptr(xt), _ffi.ptr(ut),
-            n, row, _ffi.stream_ptr(x0.device)), "cfm_flow_pairs_f32")
+        with torch.cuda.device(x0.device):
+            _ffi.check(_ffi.lib().cfm_flow_pairs_f32(
+                self._FUSED_KIND, _ffi.ptr(x0c), _ffi.ptr(x1c), _ffi.ptr(i), _ffi.ptr(j), _ffi.ptr(eps),
+                _ffi.ptr(ra), _ffi.ptr(rb), _ffi.ptr(rs), _ffi.ptr(rc), sig, kon, _ffi.ptr(xt), _ffi.ptr(ut),
+                n, row, _ffi.stream_ptr(x0.device)), "cfm_flow_pairs_f32")
         return (t, xt, ut, eps) if return_noise else (t, xt, ut)
 
     def compute_lambda(self, t):

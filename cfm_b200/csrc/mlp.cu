@@ -8,7 +8,7 @@
 //     the whole batch (utils.py:52), cat([x, t]) @ W0^T == x @ W0x^T + t * w0t, so the
 //     (B, dim+1) concatenation is never materialised and t folds into the bias;
 //   * the remaining weights / biases copied contiguously;
-//   * (algo 2) TF32 hi/lo splits of all weights for the tcgen05 path (mlp_tc.cu).
+//   * (algo 2) row-scaled fp16 (hi, lo) splits of all weights for the tcgen05 paths (mlp_h3.cu).
 // algo 1 (this file): four SIMT fp32 GEMMs with fused bias + activation epilogues (true fp32
 // FMA, the numerics of the reference's cuBLAS sgemm with TF32 off).
 #include "gemm_simt.cuh"
@@ -139,7 +139,7 @@ extern "C" int cfm_mlp_tc_supported(int batch, int dim, int w, int out_dim) {
   return mlp_tc_supported(batch, dim, w, out_dim);
 }
 
-extern "C" int cfm_mlp_forward_split_f32(const void* prepared, const float* x_hi, const float* x_lo, int batch,
+extern "C" int cfm_mlp_forward_split_f32(const void* prepared, const void* x_hi, const void* x_lo, int batch,
                                          int dim, int w, int out_dim, int time_varying, const float* t_dev,
                                          float t_host, int act, float* y, void* workspace,
                                          size_t workspace_bytes, void* stream) {

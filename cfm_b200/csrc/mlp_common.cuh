@@ -10,12 +10,12 @@ struct MlpBlobHeader {
 };
 constexpr int32_t kMlpMagic = 0x4d4c5031;  // "MLP1"
 
-size_t mlp_tc_blob_bytes(int dim, int w, int out_dim);  // mlp_tc.cu
+size_t mlp_tc_blob_bytes(int dim, int w, int out_dim);  // mlp_h3.cu
 int mlp_tc_prepare(const MlpBlobHeader& h, void* blob, cudaStream_t s);
 int mlp_tc_supported(int batch, int dim, int w, int out_dim);
 size_t mlp_tc_workspace_bytes(int batch, int dim, int w, int out_dim);
-int mlp_tc_forward(const MlpBlobHeader& h, const void* blob, const float* x, const float* x_hi,
-                   const float* x_lo, int batch, const float* t_dev, float t_host, int act, float* y, void* ws,
+int mlp_tc_forward(const MlpBlobHeader& h, const void* blob, const float* x, const void* x_hi,
+                   const void* x_lo, int batch, const float* t_dev, float t_host, int act, float* y, void* ws,
                    size_t ws_bytes, cudaStream_t s);
 
 static inline MlpBlobHeader mlp_layout(int dim, int w, int out_dim, int tv) {

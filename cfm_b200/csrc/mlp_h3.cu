@@ -1,0 +1,531 @@
+// Tensor-core paths of the vector-field MLP  y = net(cat([x, t], 1))
+// (reference: torchcfm/models/models.py:10-21 composed with torchcfm/utils.py:51-52), fp16x3 scheme of
+// gemm_h3.cuh (kind::f16 MMAs, fp32-grade accuracy: 1.8e-7 of max|y| in the CPU emulation of this network).
+//
+// (1) mlp_fused_h3_kernel -- ONE persistent launch per forward for 256-wide hidden layers (BASELINE config 3:
+//     785 -> 256 -> 256 -> 256 -> 784).  A CTA owns a 128-row slab of the batch and runs all four layers on it:
+//       layer 1   x (hi, lo) and W0 stream through a 2-stage TMA ring; 6 MMAs (N = 128) per k-step fill two
+//                 accumulator pairs (TMEM columns 0-255 / 256-511, one per half of the 256 outputs);
+//       epilogue  TMEM -> registers, (acc0 + acc1 2^-11) / weight-row scale + bias (+ t * W0[:, -1]), SELU,
+//                 fp16 (hi, lo) split, written straight into shared memory in the K-major 128B-swizzled
+//                 layout the next layer's A descriptors read (fence.proxy.async + mbarrier hand-over):
+//                 hidden activations never leave the SM;
+//       layers 2-4  A = the resident activation tile (128 x 256 hi + lo = 128 KB), B = weight tiles of
+//                 128 output units x 64 inputs streamed through a 3-stage ring; accumulator pairs are
+//                 double-buffered so the epilogue of tile n overlaps the MMAs of tile n+1; layer 4's epilogue
+//                 adds the bias and writes y.
+//     Shared memory: [0,128K) activations (layer 1: ring stage 0), [128K,224K) weight ring (layer 1: stage 1).
+// (2) per-layer launches of the generic fp16x3 GEMM (other widths), hidden activations as fp16 (hi, lo)
+//     pairs in L2.
+// Weights are split once per weight set by cfm_mlp_prepare (row-scaled by powers of two, gemm_h3.cuh).
+#include "gemm_h3.cuh"
+#include "mlp_common.cuh"
+
+namespace cfm {
+
+int prep_rows_h3(const float* X, int rows, int d, __half* hi, __half* lo, int64_t ldo, float* sqnorm,
+                 float* inv_scale, cudaStream_t s);  // sqdist_h3.cu
+
+// ---- blob: tensor-core section ------------------------------------------------------------------------
+struct H3Blob {  // byte offsets inside the blob's tensor-core section
+  size_t wh[4], wl[4], is[4], total;
+  int64_t ld[4];
+};
+static H3Blob h3_blob(int dimp, int w, int out_dim) {
+  H3Blob b;
+  const int rows[4] = {w, w, w, out_dim}, cols[4] = {dimp, w, w, w};
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 1024); return r; };
+  for (int l = 0; l < 4; ++l) {
+    b.ld[l] = (cols[l] + 7) / 8 * 8;
+    b.wh[l] = take((size_t)rows[l] * b.ld[l] * 2);
+    b.wl[l] = take((size_t)rows[l] * b.ld[l] * 2);
+    b.is[l] = take((size_t)rows[l] * 4);
+  }
+  b.total = o;
+  return b;
+}
+
+size_t mlp_tc_blob_bytes(int dim, int w, int out_dim) { return h3_blob((dim + 3) / 4 * 4, w, out_dim).total; }
+
+int mlp_tc_prepare(const MlpBlobHeader& h, void* blob, cudaStream_t s) {
+  if ((h.w & 7) != 0) return CFM_OK;  // tensor-core paths need 16-byte fp16 rows; the SIMT path serves the rest
+  char* B = reinterpret_cast<char*>(blob);
+  char* T = B + h.off_tc;
+  const H3Blob tb = h3_blob(h.dimp, h.w, h.out_dim);
+  const int64_t src[4] = {h.off_w0x, h.off_w1, h.off_w2, h.off_w3};
+  const int rows[4] = {h.w, h.w, h.w, h.out_dim}, cols[4] = {h.dimp, h.w, h.w, h.w};
+  for (int l = 0; l < 4; ++l) {
+    const int rc = prep_rows_h3(reinterpret_cast<const float*>(B + src[l]), rows[l], cols[l],
+                                reinterpret_cast<__half*>(T + tb.wh[l]), reinterpret_cast<__half*>(T + tb.wl[l]),
+                                tb.ld[l], nullptr, reinterpret_cast<float*>(T + tb.is[l]), s);
+    if (rc != CFM_OK) return rc;
+  }
+  return CFM_OK;
+}
+
+int mlp_tc_supported(int batch, int dim, int w, int out_dim) {
+  // 16-byte aligned fp16 rows for the TMA maps, float4 rows for y; tiny problems stay on the SIMT path
+  return batch >= 128 && dim >= 32 && (dim % 8 == 0) && (w % 8 == 0) && w >= 32 && (out_dim % 4 == 0);
+}
+static bool fused_supported(int batch, int dim, int w, int out_dim) {
+  return mlp_tc_supported(batch, dim, w, out_dim) && w == 256 && dim >= 64;
+}
+
+// x -> fp16 (hi, lo), unscaled and saturating (activation-side operands carry no row scale)
+__global__ void split_h3_sat_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo,
+                                    int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    __half h, l;
+    split_h3_sat(x[i], h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+static int split_h3_launch(const float* x, __half* hi, __half* lo, int64_t n, cudaStream_t s) {
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  split_h3_sat_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, hi, lo, n); ::cfm::note_launches(1);
+  CFM_CUDA_OK(cudaGetLastError());
+  return CFM_OK;
+}
+
+// pack 8 floats' worth of fp16 into one 16-byte word
+__device__ __forceinline__ uint4 pack8(const __half (&h)[8]) {
+  return make_uint4((uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
+                    (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16),
+                    (uint32_t)__half_as_ushort(h[4]) | ((uint32_t)__half_as_ushort(h[5]) << 16),
+                    (uint32_t)__half_as_ushort(h[6]) | ((uint32_t)__half_as_ushort(h[7]) << 16));
+}
+
+// ======================================================================================================
+// (2) per-layer epilogue for the generic GEMM core
+// ======================================================================================================
+struct MlpH3Epilogue {
+  const float* bias;
+  const float* inv_ws;  // 1 / weight-row scale, per output column
+  const float* tcol;    // nullable: + t * tcol[col]
+  const float* t_dev;   // nullable device scalar
+  float t_host;
+  int act;              // -1: none
+  float* out;           // nullable: plain fp32 result (last layer)
+  __half* out_hi;       // nullable: fp16 (hi, lo) split of the result (hidden layers)
+  __half* out_lo;
+  int64_t ldo;
+  float t;
+  __device__ __forceinline__ void begin_row(int, bool) { t = tcol ? (t_dev ? __ldg(t_dev) : t_host) : 0.f; }
+  __device__ __forceinline__ float one(float acc, float is, float b, float tc) const {
+    float v = fmaf(acc, is, b);
+    if (tcol) v = fmaf(t, tc, v);
+    return act >= 0 ? act_apply_fast(v, act) : v;
+  }
+  __device__ __forceinline__ void store32(int row0, int lane, int col0, const float (&r)[32], int n0, int n1,
+                                          float* tile) {
+    const int row = row0 + lane;
+    if ((col0 + 32 <= n1) && ((ldo & 3) == 0) && (out_hi == nullptr || (ldo & 7) == 0)) {
+      float o[32];
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + c));
+        const float4 is = __ldg(reinterpret_cast<const float4*>(inv_ws + col0 + c));
+        float4 tc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tcol) tc4 = __ldg(reinterpret_cast<const float4*>(tcol + col0 + c));
+        o[c] = one(r[c], is.x, b.x, tc4.x); o[c + 1] = one(r[c + 1], is.y, b.y, tc4.y);
+        o[c + 2] = one(r[c + 2], is.z, b.z, tc4.z); o[c + 3] = one(r[c + 3], is.w, b.w, tc4.w);
+      }
+      const int64_t base = (int64_t)row0 * ldo + col0;
+      if (out) tc_store_chunk32(tile, o, out + base, ldo, n0 - row0, lane);
+      if (out_hi && row < n0) {  // 64 contiguous bytes per row and array
+        __half* ph = out_hi + (int64_t)row * ldo + col0;
+        __half* pl = out_lo + (int64_t)row * ldo + col0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          __half hh[8], ll[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) split_h3_sat(o[8 * g + c], hh[c], ll[c]);
+          *reinterpret_cast<uint4*>(ph + 8 * g) = pack8(hh);
+          *reinterpret_cast<uint4*>(pl + 8 * g) = pack8(ll);
+        }
+      }
+    } else if (row < n0) {
+      const int64_t base = (int64_t)row * ldo + col0;
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (col0 + c < n1) {
+          const float v = one(r[c], __ldg(inv_ws + col0 + c), __ldg(bias + col0 + c), tcol ? __ldg(tcol + col0 + c) : 0.f);
+          if (out) out[base + c] = v;
+          if (out_hi) { __half hh, ll; split_h3_sat(v, hh, ll); out_hi[base + c] = hh; out_lo[base + c] = ll; }
+        }
+    }
+  }
+  __device__ __forceinline__ void finish(int) {}
+};
+
+// ======================================================================================================
+// (1) the fused four-layer kernel (hidden width 256)
+// ======================================================================================================
+constexpr int kFW = 256;                       // hidden width
+constexpr int kFActBytes = 2 * kTM * kFW * 2;  // 128 KB: hi [4 chunks x 16 KB] | lo [4 chunks x 16 KB]
+constexpr int kFRingStage = 2 * 128 * kHK * 2; // 32 KB: B_hi | B_lo of one 128 x 64 weight tile
+constexpr int kFRingStages = 3;
+constexpr int kFL1Stage = 2 * kHABytes + 2 * kFW * kHK * 2;  // 96 KB: x_hi | x_lo | W0_hi (256 rows) | W0_lo
+constexpr size_t kFSmemBytes = kFActBytes + kFRingStages * kFRingStage + 256;
+constexpr uint32_t kFIdesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);  // M=128, N=128
+
+struct FusedParams {
+  int batch, dim, out_dim, act;
+  const float* bias[4];
+  const float* inv_ws[4];
+  const float* tcol;    // W0[:, -1] or null
+  const float* t_dev;   // device scalar or null
+  float t_host;
+  float* y;             // (batch, out_dim) fp32
+};
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
+                    const __grid_constant__ CUtensorMap map_w0h, const __grid_constant__ CUtensorMap map_w0l,
+                    const __grid_constant__ CUtensorMap map_w1h, const __grid_constant__ CUtensorMap map_w1l,
+                    const __grid_constant__ CUtensorMap map_w2h, const __grid_constant__ CUtensorMap map_w2l,
+                    const __grid_constant__ CUtensorMap map_w3h, const __grid_constant__ CUtensorMap map_w3l,
+                    const FusedParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* act = smem;                       // [0, 128K)
+  uint8_t* ring = smem + kFActBytes;         // [128K, 224K)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kFActBytes + kFRingStages * kFRingStage);
+  uint64_t* l1_full = bars;          // [2]
+  uint64_t* l1_empty = bars + 2;     // [2]
+  uint64_t* r_full = bars + 4;       // [3]
+  uint64_t* r_empty = bars + 7;      // [3]
+  uint64_t* tfull = bars + 10;       // [2] accumulator pair complete
+  uint64_t* tempty = bars + 12;      // [2] accumulator pair drained
+  uint64_t* act_ready = bars + 14;   // [2] activation columns 0-127 / 128-255 of the current layer are in smem
+  uint64_t* slab_done = bars + 16;   // [1] every MMA of the slab has retired
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 17);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_slabs = (p.batch + kTM - 1) / kTM;
+  const int nk1 = (p.dim + kHK - 1) / kHK;
+  const int t4 = (p.out_dim + 127) / 128;   // layer-4 tiles
+  const int tiles_per_slab = 6 + t4;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(&l1_full[s], 1); mbar_init(&l1_empty[s], 1); }
+    for (int s = 0; s < kFRingStages; ++s) { mbar_init(&r_full[s], 1); mbar_init(&r_empty[s], 1); }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 32 * kEpiWarps);
+      mbar_init(&act_ready[a], 32 * kEpiWarps);
+    }
+    mbar_init(slab_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t q1 = 0, qr = 0;  // running chunk counters of the layer-1 ring and the weight ring
+      uint32_t g = 0;           // running tile counter (accumulator pair = g & 1)
+      int it = 0;
+      for (int slab = blockIdx.x; slab < num_slabs; slab += gridDim.x, ++it) {
+        // the layer-1 stages overlay the activation tile and the weight ring: the previous slab's MMAs must be done
+        if (it > 0) mbar_wait(slab_done, (uint32_t)((it - 1) & 1));
+        for (int kc = 0; kc < nk1; ++kc, ++q1) {
+          const int s = q1 & 1;
+          mbar_wait(&l1_empty[s], ((q1 >> 1) & 1) ^ 1);
+          uint8_t* sb = s == 0 ? act : ring;
+          mbar_expect_tx(&l1_full[s], kFL1Stage);
+          tma_load_2d(sb, &map_xh, &l1_full[s], kc * kHK, slab * kTM);
+          tma_load_2d(sb + kHABytes, &map_xl, &l1_full[s], kc * kHK, slab * kTM);
+          tma_load_2d(sb + 2 * kHABytes, &map_w0h, &l1_full[s], kc * kHK, 0);
+          tma_load_2d(sb + 2 * kHABytes + kFW * kHK * 2, &map_w0l, &l1_full[s], kc * kHK, 0);
+        }
+        // layer 1's last MMA has retired (its accumulators are complete): the weight ring is free
+        mbar_wait(&tfull[g & 1], (g >> 1) & 1);
+        g += 2;
+        for (int layer = 2; layer <= 4; ++layer) {
+          const CUtensorMap* mh = layer == 2 ? &map_w1h : layer == 3 ? &map_w2h : &map_w3h;
+          const CUtensorMap* ml = layer == 2 ? &map_w1l : layer == 3 ? &map_w2l : &map_w3l;
+          const int nt = layer < 4 ? 2 : t4;
+          for (int n = 0; n < nt; ++n, ++g) {
+            for (int kc = 0; kc < kFW / kHK; ++kc, ++qr) {
+              const int s = qr % kFRingStages;
+              mbar_wait(&r_empty[s], ((qr / kFRingStages) & 1) ^ 1);
+              uint8_t* sb = ring + s * kFRingStage;
+              mbar_expect_tx(&r_full[s], kFRingStage);
+              tma_load_2d(sb, mh, &r_full[s], kc * kHK, n * 128);
+              tma_load_2d(sb + kFRingStage / 2, ml, &r_full[s], kc * kHK, n * 128);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    uint32_t q1 = 0, qr = 0, g = 0, ar = 0;  // ar: running count of hidden-layer hand-overs (act_ready phase)
+    int done_slabs = 0;
+    for (int slab = blockIdx.x; slab < num_slabs; slab += gridDim.x, ++done_slabs) {
+      // ---- layer 1: both accumulator pairs at once ----
+      mbar_wait(&tempty[g & 1], ((g >> 1) & 1) ^ 1);
+      mbar_wait(&tempty[(g + 1) & 1], (((g + 1) >> 1) & 1) ^ 1);
+      tc_fence_after();
+      for (int kc = 0; kc < nk1; ++kc, ++q1) {
+        const int s = q1 & 1;
+        mbar_wait(&l1_full[s], (q1 >> 1) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(s == 0 ? act : ring);
+          const uint64_t ah = umma_desc_sw128(sa), al = umma_desc_sw128(sa + kHABytes);
+#pragma unroll
+          for (int n = 0; n < 2; ++n) {
+            const uint32_t b = (uint32_t)((g + n) & 1);
+            const uint32_t d0 = tmem_base + b * 256u, d1 = d0 + 128u;
+            const uint64_t bh = umma_desc_sw128(sa + 2 * kHABytes + n * 128 * 128);
+            const uint64_t bl = umma_desc_sw128(sa + 2 * kHABytes + kFW * kHK * 2 + n * 128 * 128);
+#pragma unroll
+            for (int k = 0; k < kHK / 16; ++k) {
+              const uint64_t koff = (uint64_t)((k * 32) >> 4);
+              const uint32_t first = (kc | k) ? 1u : 0u;
+              tc_mma_f16(d1, ah + koff, bl + koff, kFIdesc, first);
+              tc_mma_f16(d1, al + koff, bh + koff, kFIdesc, 1u);
+              tc_mma_f16(d0, ah + koff, bh + koff, kFIdesc, first);
+            }
+          }
+          tc_commit(&l1_empty[s]);
+          if (kc == nk1 - 1) { tc_commit(&tfull[g & 1]); tc_commit(&tfull[(g + 1) & 1]); }
+        }
+        __syncwarp();
+      }
+      g += 2;
+      // ---- layers 2-4: A = resident activations, B = streamed weight tiles ----
+      for (int layer = 2; layer <= 4; ++layer, ++ar) {
+        const int nt = layer < 4 ? 2 : t4;
+        for (int n = 0; n < nt; ++n, ++g) {
+          const uint32_t b = g & 1;
+          mbar_wait(&tempty[b], ((g >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d0 = tmem_base + b * 256u, d1 = d0 + 128u;
+          for (int kc = 0; kc < kFW / kHK; ++kc, ++qr) {
+            if (n == 0 && (kc & 1) == 0) {  // activation columns [128 (kc/2), +128) written and visible to the MMA proxy
+              mbar_wait(&act_ready[kc >> 1], ar & 1);
+              tc_fence_after();
+            }
+            const int s = qr % kFRingStages;
+            mbar_wait(&r_full[s], (qr / kFRingStages) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+              const uint32_t sa = smem_u32(act) + kc * kHABytes;
+              const uint64_t ah = umma_desc_sw128(sa), al = umma_desc_sw128(sa + kFActBytes / 2);
+              const uint32_t sbp = smem_u32(ring + s * kFRingStage);
+              const uint64_t bh = umma_desc_sw128(sbp), bl = umma_desc_sw128(sbp + kFRingStage / 2);
+#pragma unroll
+              for (int k = 0; k < kHK / 16; ++k) {
+                const uint64_t koff = (uint64_t)((k * 32) >> 4);
+                const uint32_t first = (kc | k) ? 1u : 0u;
+                tc_mma_f16(d1, ah + koff, bl + koff, kFIdesc, first);
+                tc_mma_f16(d1, al + koff, bh + koff, kFIdesc, 1u);
+                tc_mma_f16(d0, ah + koff, bh + koff, kFIdesc, first);
+              }
+              tc_commit(&r_empty[s]);
+              if (kc == kFW / kHK - 1) tc_commit(&tfull[b]);
+            }
+            __syncwarp();
+          }
+        }
+      }
+      if (lane == 0) tc_commit(slab_done);
+      __syncwarp();
+    }
+    // no asynchronous arrive may still be in flight towards this CTA's shared memory when it exits
+    if (done_slabs > 0) mbar_wait(slab_done, (uint32_t)((done_slabs - 1) & 1));
+  } else {
+    // ===================== epilogue (warps 2..9) =====================
+    const int quad = warp & 3;          // TMEM lane quadrant
+    const int half = (warp - 2) >> 2;   // 64-column half of the 128-column tile
+    const int r_in = quad * 32 + lane;  // row inside the slab
+    uint32_t g = 0;
+    for (int slab = blockIdx.x; slab < num_slabs; slab += gridDim.x) {
+      const int row = slab * kTM + r_in;
+      const float t = p.tcol ? (p.t_dev ? __ldg(p.t_dev) : p.t_host) : 0.f;
+      for (int tl = 0; tl < tiles_per_slab; ++tl, ++g) {
+        const int layer = tl < 6 ? (tl >> 1) + 1 : 4;
+        const int n = tl < 6 ? (tl & 1) : tl - 6;
+        const uint32_t b = g & 1;
+        mbar_wait(&tfull[b], (g >> 1) & 1);
+        if (layer < 4 && n == 0) {
+          // this layer's other tile still reads the activations this epilogue is about to overwrite
+          mbar_wait(&tfull[(g + 1) & 1], ((g + 1) >> 1) & 1);
+        }
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + b * 256u + (uint32_t)(half * 64);
+        const float* bias = p.bias[layer - 1];
+        const float* inv_ws = p.inv_ws[layer - 1];
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t r0[32], r1[32];
+          tc_ld32_nowait(taddr + c0, r0);
+          tc_ld32_nowait(taddr + 128 + c0, r1);
+          tc_ld_wait();
+          const int col0 = n * 128 + half * 64 + c0;  // column of this layer's output
+          float o[32];
+          if (layer < 4 || col0 + 32 <= p.out_dim) {
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col0 + c));
+              const float4 is = __ldg(reinterpret_cast<const float4*>(inv_ws + col0 + c));
+              float4 tc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (layer == 1 && p.tcol) tc4 = __ldg(reinterpret_cast<const float4*>(p.tcol + col0 + c));
+              const float isv[4] = {is.x, is.y, is.z, is.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+              const float tv[4] = {tc4.x, tc4.y, tc4.z, tc4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float acc = fmaf(__uint_as_float(r1[c + e]), kH3InvScale, __uint_as_float(r0[c + e]));
+                float v = fmaf(acc, isv[e], bv[e]);
+                if (layer == 1) v = fmaf(t, tv[e], v);
+                o[c + e] = layer < 4 ? act_apply_fast(v, p.act) : v;
+              }
+            }
+            if (layer < 4) {
+              // activations -> shared memory, K-major 128B-swizzled operand layout:
+              // chunk kc = col / 64 (16 KB each), row r at r * 128 B, 16-byte unit u stored at u ^ (r & 7)
+              const int kc = col0 >> 6, u0 = (col0 & 63) >> 3;
+              uint8_t* bh = act + kc * kHABytes + r_in * 128;
+              uint8_t* bl = bh + kFActBytes / 2;
+#pragma unroll
+              for (int gq = 0; gq < 4; ++gq) {
+                __half hh[8], ll[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) split_h3_sat(o[8 * gq + c], hh[c], ll[c]);
+                const int off = ((u0 + gq) ^ (r_in & 7)) << 4;
+                *reinterpret_cast<uint4*>(bh + off) = pack8(hh);
+                *reinterpret_cast<uint4*>(bl + off) = pack8(ll);
+              }
+            } else if (row < p.batch) {
+              float4* dst = reinterpret_cast<float4*>(p.y + (int64_t)row * p.out_dim + col0);
+#pragma unroll
+              for (int c = 0; c < 8; ++c) dst[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+            }
+          } else if (row < p.batch) {  // ragged tail of the last layer-4 tile
+            for (int c = 0; c < 32; ++c)
+              if (col0 + c < p.out_dim) {
+                const float acc = fmaf(__uint_as_float(r1[c]), kH3InvScale, __uint_as_float(r0[c]));
+                p.y[(int64_t)row * p.out_dim + col0 + c] = fmaf(acc, __ldg(inv_ws + col0 + c), __ldg(bias + col0 + c));
+              }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty[b]);
+        if (layer < 4) {
+          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core's async proxy
+          mbar_arrive(&act_ready[n]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---- workspace ----------------------------------------------------------------------------------------
+struct H3MlpWs { size_t xh, xl, ah, al, bh, bl, total; };
+static H3MlpWs h3_mlp_ws(int batch, int dim, int w) {
+  H3MlpWs t;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 1024); return r; };
+  t.xh = take((size_t)batch * dim * 2); t.xl = take((size_t)batch * dim * 2);
+  t.ah = take((size_t)batch * w * 2); t.al = take((size_t)batch * w * 2);
+  t.bh = take((size_t)batch * w * 2); t.bl = take((size_t)batch * w * 2);
+  t.total = o;
+  return t;
+}
+size_t mlp_tc_workspace_bytes(int batch, int dim, int w, int) { return h3_mlp_ws(batch, dim, w).total; }
+
+static int fused_mode() {  // CFM_MLP_FUSED=0 forces the per-layer launches (A/B experiments)
+  static int m = -1;
+  if (m < 0) { const char* e = getenv("CFM_MLP_FUSED"); m = e ? atoi(e) : 1; }
+  return m;
+}
+
+int mlp_tc_forward(const MlpBlobHeader& h, const void* blob, const float* x, const void* x_hi_v,
+                   const void* x_lo_v, int batch, const float* t_dev, float t_host, int act, float* y, void* ws,
+                   size_t ws_bytes, cudaStream_t s) {
+  const H3MlpWs W = h3_mlp_ws(batch, h.dim, h.w);
+  CFM_REQUIRE(ws_bytes >= W.total, "mlp tcgen05: workspace too small (%zu < %zu)", ws_bytes, W.total);
+  CFM_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x_hi_v) | reinterpret_cast<uintptr_t>(x_lo_v) |
+                reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(ws)) & 15) == 0,
+              "mlp tcgen05: x, y and the workspace must be 16-byte aligned");
+  const char* B = reinterpret_cast<const char*>(blob);
+  const char* T = B + h.off_tc;
+  const H3Blob tb = h3_blob(h.dimp, h.w, h.out_dim);
+  char* w = reinterpret_cast<char*>(ws);
+  auto F = [&](int64_t off) { return reinterpret_cast<const float*>(B + off); };
+  auto WH = [&](int l) { return reinterpret_cast<const __half*>(T + tb.wh[l]); };
+  auto WL = [&](int l) { return reinterpret_cast<const __half*>(T + tb.wl[l]); };
+  auto IS = [&](int l) { return reinterpret_cast<const float*>(T + tb.is[l]); };
+  auto Hp = [&](size_t off) { return reinterpret_cast<__half*>(w + off); };
+  int rc;
+  const __half* xh = reinterpret_cast<const __half*>(x_hi_v);
+  const __half* xl = reinterpret_cast<const __half*>(x_lo_v);
+  if (xh == nullptr) {  // plain fp32 input: split it here; otherwise the caller (the RK stage kernel) already did
+    if ((rc = split_h3_launch(x, Hp(W.xh), Hp(W.xl), (int64_t)batch * h.dim, s)) != CFM_OK) return rc;
+    xh = Hp(W.xh); xl = Hp(W.xl);
+  }
+  const float* tcol = h.time_varying ? F(h.off_w0t) : nullptr;
+  const int64_t boff[4] = {h.off_b0, h.off_b1, h.off_b2, h.off_b3};
+
+  if (fused_mode() && fused_supported(batch, h.dim, h.w, h.out_dim)) {
+    CUtensorMap mx[2], mw[8];
+    if ((rc = tc_make_map_f16(&mx[0], xh, batch, h.dim, (int64_t)h.dim, kTM)) != CFM_OK) return rc;
+    if ((rc = tc_make_map_f16(&mx[1], xl, batch, h.dim, (int64_t)h.dim, kTM)) != CFM_OK) return rc;
+    const int rows[4] = {h.w, h.w, h.w, h.out_dim}, cols[4] = {h.dim, h.w, h.w, h.w};
+    for (int l = 0; l < 4; ++l) {
+      const int box = l == 0 ? 256 : 128;
+      if ((rc = tc_make_map_f16(&mw[2 * l], WH(l), rows[l], cols[l], tb.ld[l], box)) != CFM_OK) return rc;
+      if ((rc = tc_make_map_f16(&mw[2 * l + 1], WL(l), rows[l], cols[l], tb.ld[l], box)) != CFM_OK) return rc;
+    }
+    FusedParams p;
+    p.batch = batch; p.dim = h.dim; p.out_dim = h.out_dim; p.act = act;
+    for (int l = 0; l < 4; ++l) { p.bias[l] = F(boff[l]); p.inv_ws[l] = IS(l); }
+    p.tcol = tcol; p.t_dev = t_dev; p.t_host = t_host; p.y = y;
+    CFM_CUDA_OK(cudaFuncSetAttribute(mlp_fused_h3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFSmemBytes));
+    int grid = (batch + kTM - 1) / kTM;
+    if (grid > sm_count()) grid = sm_count();
+    mlp_fused_h3_kernel<<<grid, kTcThreads, kFSmemBytes, s>>>(mx[0], mx[1], mw[0], mw[1], mw[2], mw[3], mw[4], mw[5],
+                                                              mw[6], mw[7], p);
+    ::cfm::note_launches(1);
+    CFM_CUDA_OK(cudaGetLastError());
+    return CFM_OK;
+  }
+
+  // per-layer launches of the generic core
+  MlpH3Epilogue e0{F(boff[0]), IS(0), tcol, t_dev, t_host, act, nullptr, Hp(W.ah), Hp(W.al), (int64_t)h.w, 0.f};
+  if ((rc = launch_gemm_h3<128>(xh, xl, batch, (int64_t)h.dim, WH(0), WL(0), h.w, tb.ld[0], h.dim, e0, s)) != CFM_OK) return rc;
+  MlpH3Epilogue e1{F(boff[1]), IS(1), nullptr, nullptr, 0.f, act, nullptr, Hp(W.bh), Hp(W.bl), (int64_t)h.w, 0.f};
+  if ((rc = launch_gemm_h3<128>(Hp(W.ah), Hp(W.al), batch, (int64_t)h.w, WH(1), WL(1), h.w, tb.ld[1], h.w, e1, s)) != CFM_OK) return rc;
+  MlpH3Epilogue e2{F(boff[2]), IS(2), nullptr, nullptr, 0.f, act, nullptr, Hp(W.ah), Hp(W.al), (int64_t)h.w, 0.f};
+  if ((rc = launch_gemm_h3<128>(Hp(W.bh), Hp(W.bl), batch, (int64_t)h.w, WH(2), WL(2), h.w, tb.ld[2], h.w, e2, s)) != CFM_OK) return rc;
+  MlpH3Epilogue e3{F(boff[3]), IS(3), nullptr, nullptr, 0.f, -1, y, nullptr, nullptr, (int64_t)h.out_dim, 0.f};
+  return launch_gemm_h3<128>(Hp(W.ah), Hp(W.al), batch, (int64_t)h.w, WH(3), WL(3), h.out_dim, tb.ld[3], h.w, e3, s);
+}
+
+}  // namespace cfm

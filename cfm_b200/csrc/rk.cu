@@ -11,9 +11,20 @@
 //
 // Buffers (fp32, numel = B*D each): x, xnew, xs (stage input), k[0..6] contiguous (k1..k7).
 // All elementwise kernels are HBM-bound: float4 accesses, grid = 4 CTAs/SM, grid-stride loops.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace cfm {
+
+// fp16x3 operand split (gemm_h3.cuh): hi = fp16(v), lo = fp16((v - hi) * 2^11), saturating
+__device__ __forceinline__ void rk_split_h3(float v, __half& hi, __half& lo) {
+  const float c = fminf(fmaxf(v, -65504.f), 65504.f);
+  hi = __float2half_rn(c);
+  const float r = (v - __half2float(hi)) * 2048.f;
+  lo = __float2half_rn(fminf(fmaxf(r, -65504.f), 65504.f));
+}
+
 
 __constant__ float kC[7] = {0.f, 1.f / 5, 3.f / 10, 4.f / 5, 8.f / 9, 1.f, 1.f};
 __constant__ float kA[7][6] = {
@@ -53,7 +64,7 @@ __device__ __forceinline__ double block_sum_to(double v, double* smem32) {
 // xs (stage 1..5) or xnew (stage 6) = x + dt * sum_j a[stage][j] * k_j ; also t_stage = t + c*dt
 __global__ void rk_stage_input_kernel(const cfm_rk_state* __restrict__ st, const float* __restrict__ x,
                                       const float* __restrict__ k, float* __restrict__ out,
-                                      float* __restrict__ out_hi, float* __restrict__ out_lo,
+                                      __half* __restrict__ out_hi, __half* __restrict__ out_lo,
                                       float* __restrict__ t_stage, int64_t numel, int stage) {
   if (st->done) return;
   const float dt = st->dt;
@@ -75,18 +86,22 @@ __global__ void rk_stage_input_kernel(const cfm_rk_state* __restrict__ st, const
     }
     if (out) reinterpret_cast<float4*>(out)[i] = v;
     if (out_hi) {  // operand pair for the tensor-core MLP: the fp32 stage input is never re-read
-      float4 h, l;
-      split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
-      split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-      reinterpret_cast<float4*>(out_hi)[i] = h;
-      reinterpret_cast<float4*>(out_lo)[i] = l;
+      __half h[4], l[4];
+      rk_split_h3(v.x, h[0], l[0]); rk_split_h3(v.y, h[1], l[1]);
+      rk_split_h3(v.z, h[2], l[2]); rk_split_h3(v.w, h[3], l[3]);
+      reinterpret_cast<uint2*>(out_hi)[i] = make_uint2(
+          (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
+          (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
+      reinterpret_cast<uint2*>(out_lo)[i] = make_uint2(
+          (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16),
+          (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16));
     }
   }
   for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
     float v = x[i];
     for (int j = 0; j < stage; ++j) v = fmaf(a[j], k[(int64_t)j * numel + i], v);
     if (out) out[i] = v;
-    if (out_hi) { float h, l; split_tf32(v, h, l); out_hi[i] = h; out_lo[i] = l; }
+    if (out_hi) { __half h, l; rk_split_h3(v, h, l); out_hi[i] = h; out_lo[i] = l; }
   }
 }
 
@@ -210,8 +225,8 @@ __device__ __forceinline__ float rk_h0(const double* scratch, int64_t numel) {
 }
 __global__ void rk_init_probe(cfm_rk_state* st, const float* __restrict__ x, const float* __restrict__ f0,
                               float* __restrict__ x_probe, float* __restrict__ t_stage,
-                              const double* __restrict__ scratch, int64_t numel) {
-  const float h0 = rk_h0(scratch, numel);
+                              const double* __restrict__ scratch, int64_t numel, int64_t numel_global) {
+  const float h0 = rk_h0(scratch, numel_global);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     st->dt_old = h0;
     if (t_stage) *t_stage = st->t + h0;
@@ -265,14 +280,14 @@ using namespace cfm;
 #define RK_CHECK(cond) CFM_REQUIRE(cond, "%s: bad argument (" #cond ")", __func__)
 
 extern "C" int cfm_rk_stage_input(const cfm_rk_state* st, const float* x, const float* k, float* out,
-                                  float* out_hi, float* out_lo, float* t_stage, int64_t numel, int stage,
+                                  void* out_hi, void* out_lo, float* t_stage, int64_t numel, int stage,
                                   void* stream) {
   RK_CHECK(st && x && k && (out || out_hi) && numel > 0 && stage >= 1 && stage <= 6);
   RK_CHECK((out_hi == nullptr) == (out_lo == nullptr));
   RK_CHECK(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(out) |
              reinterpret_cast<uintptr_t>(out_hi) | reinterpret_cast<uintptr_t>(out_lo)) & 15) == 0);
-  rk_stage_input_kernel<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(st, x, k, out, out_hi, out_lo, t_stage,
-                                                                         numel, stage); ::cfm::note_launches(1);
+  rk_stage_input_kernel<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(
+      st, x, k, out, reinterpret_cast<__half*>(out_hi), reinterpret_cast<__half*>(out_lo), t_stage, numel, stage); ::cfm::note_launches(1);
   CFM_CUDA_OK(cudaGetLastError());
   return CFM_OK;
 }
@@ -298,20 +313,44 @@ extern "C" int cfm_rk_commit(const cfm_rk_state* st, float* x, const float* xnew
 }
 extern "C" int cfm_rk_init_a(cfm_rk_state* st, const float* x, const float* f0, float* x_probe,
                              float* t_stage, double* scratch, int64_t numel, void* stream) {
-  RK_CHECK(st && x && f0 && x_probe && scratch && numel > 0);
-  cudaStream_t s = (cudaStream_t)stream;
-  CFM_CUDA_OK(cudaMemsetAsync(scratch, 0, 4 * sizeof(double), s));
-  rk_init_reduce_a<<<ew_grid(numel), 256, 0, s>>>(st, x, f0, scratch, numel); ::cfm::note_launches(1);
-  rk_init_probe<<<ew_grid(numel), 256, 0, s>>>(st, x, f0, x_probe, t_stage, scratch, numel); ::cfm::note_launches(1);
-  CFM_CUDA_OK(cudaGetLastError());
-  return CFM_OK;
+  int rc = cfm_rk_init_sums(st, x, f0, nullptr, scratch, numel, 0, stream);
+  if (rc != CFM_OK) return rc;
+  return cfm_rk_init_probe(st, x, f0, x_probe, t_stage, scratch, numel, numel, stream);
 }
 extern "C" int cfm_rk_init_b(cfm_rk_state* st, const float* x, const float* f0, const float* f1,
                              const float* t_span, double* scratch, int64_t numel, void* stream) {
-  RK_CHECK(st && x && f0 && f1 && t_span && scratch && numel > 0);
+  int rc = cfm_rk_init_sums(st, x, f0, f1, scratch, numel, 1, stream);
+  if (rc != CFM_OK) return rc;
+  return cfm_rk_init_finish(st, t_span, scratch, numel, stream);
+}
+// the same four steps one by one, so that a sharded (lock-step) driver can all-reduce the partial sums in
+// `scratch` between them and pass the GLOBAL element count to the steps that turn sums into norms
+extern "C" int cfm_rk_init_sums(const cfm_rk_state* st, const float* x, const float* f0, const float* f1,
+                                double* scratch, int64_t numel, int phase, void* stream) {
+  RK_CHECK(st && x && f0 && scratch && numel > 0 && (phase == 0 || (phase == 1 && f1)));
   cudaStream_t s = (cudaStream_t)stream;
-  rk_init_reduce_b<<<ew_grid(numel), 256, 0, s>>>(st, x, f0, f1, scratch, numel); ::cfm::note_launches(1);
-  rk_init_finish<<<1, 1, 0, s>>>(st, t_span, scratch, numel); ::cfm::note_launches(1);
+  if (phase == 0) {
+    CFM_CUDA_OK(cudaMemsetAsync(scratch, 0, 4 * sizeof(double), s));
+    rk_init_reduce_a<<<ew_grid(numel), 256, 0, s>>>(st, x, f0, scratch, numel); ::cfm::note_launches(1);
+  } else {
+    rk_init_reduce_b<<<ew_grid(numel), 256, 0, s>>>(st, x, f0, f1, scratch, numel); ::cfm::note_launches(1);
+  }
+  CFM_CUDA_OK(cudaGetLastError());
+  return CFM_OK;
+}
+extern "C" int cfm_rk_init_probe(cfm_rk_state* st, const float* x, const float* f0, float* x_probe,
+                                 float* t_stage, const double* scratch, int64_t numel, int64_t numel_global,
+                                 void* stream) {
+  RK_CHECK(st && x && f0 && x_probe && scratch && numel > 0 && numel_global >= numel);
+  rk_init_probe<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(st, x, f0, x_probe, t_stage, scratch, numel,
+                                                                 numel_global); ::cfm::note_launches(1);
+  CFM_CUDA_OK(cudaGetLastError());
+  return CFM_OK;
+}
+extern "C" int cfm_rk_init_finish(cfm_rk_state* st, const float* t_span, const double* scratch,
+                                  int64_t numel_global, void* stream) {
+  RK_CHECK(st && t_span && scratch && numel_global > 0);
+  rk_init_finish<<<1, 1, 0, (cudaStream_t)stream>>>(st, t_span, scratch, numel_global); ::cfm::note_launches(1);
   CFM_CUDA_OK(cudaGetLastError());
   return CFM_OK;
 }

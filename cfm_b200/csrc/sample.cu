@@ -162,13 +162,123 @@ __global__ void draw_kernel(E ent, int n0, int n1, const double* __restrict__ ro
 
 // ---- fast draw for Sinkhorn potentials whose last update was the row update ---------------------
 // Row masses are then exactly a_i = 1/n0 by construction (u_i = log a_i - LSE_j(...)), so the row is
-// i = floor(u * n0) and only the within-row inversion needs the plan: weights w_j = ex2(M_ij*c2 + v2_j)
-// (the u_i factor cancels in the row-normalised cdf).  One warp per draw, two coalesced float4 passes
-// over the row (the second one hits L1/L2): pass A totals the row, pass B walks 1024-column blocks
-// to the one holding the target and resolves it with a warp scan.
+// i = floor(u * n0) and only the within-row inversion needs the plan.  The weights are the plan entries
+// themselves,  w_j = pi_ij = exp(-M_ij/reg + lu_i + lv_j)  (<= a_i, and their row sum is a_i): every
+// exponent is <= 0 and the largest one is >= -log(n0 n1), so a row can neither overflow nor underflow
+// whatever |M/reg| is (the first version normalised by lv_0 only; its exponent  -M_ij/reg + lv_j - lv_0
+// = log pi_ij - (lu_i + lv_0)  is O(M/reg) and under/overflowed fp32 whole rows for M/reg >~ 100).
+// Two exponent flavours, selected on the device by the same rule as the solver (|M/reg| <= 64: fp32):
+//   fast     x = M*c2 + (lv2_j + lu2_i) in fp32 log2 units (all terms <~ 100)
+//   precise  x = (double)(-(M / cmax) / reg) + lu_i + lv_j with NumPy's fp32 roundings of the quotients and
+//            float64 adds (terms are ~1e4 and cancel to ~ -10), then one fp32 ex2
+// When no log_u is available (row-conditional draws of an arbitrary potential pair) a first pass takes
+// the row maximum of -M_ij/reg + lv_j instead.  One warp per draw, coalesced float4 passes over the row
+// (after the first they hit L1/L2): pass A totals the row, pass B walks 1024-column blocks to the one
+// holding the target and resolves it with a warp scan.
+template <bool F64>
+struct RowWeight {
+  const float* row;
+  const double* lv;
+  float c2, reg, cmax;
+  int normalize;
+  float shift32;    // fast: lu2_i (or -rowmax) in log2 units
+  double shift64;   // precise: lu_i (or -rowmax) in natural-log units
+  __device__ __forceinline__ float expo(float m, int j) const {  // log2 of the (shifted) weight
+    if (F64) {
+      const float mn = normalize ? __fdiv_rn(m, cmax) : m;
+      return (float)(((double)(-__fdiv_rn(mn, reg)) + shift64 + lv[j]) * kLog2ed);
+    }
+    return fmaf(m, c2, (float)(lv[j] * kLog2ed) + shift32);
+  }
+  __device__ __forceinline__ float one(int j) const { return ex2f(expo(__ldg(row + j), j)); }
+  __device__ __forceinline__ float4 four(int j) const {
+    const float4 m = *reinterpret_cast<const float4*>(row + j);
+    return make_float4(ex2f(expo(m.x, j)), ex2f(expo(m.y, j + 1)), ex2f(expo(m.z, j + 2)), ex2f(expo(m.w, j + 3)));
+  }
+};
+
+template <bool F64>
+__device__ __forceinline__ int draw_in_row(RowWeight<F64>& W, bool have_shift, int n1, bool vec, double frac,
+                                           int lane, int32_t* status) {
+  if (!have_shift) {  // pass 0: row maximum of the exponent, so that the largest weight is 1
+    W.shift32 = 0.f; W.shift64 = 0.0;
+    float mx = -3.0e38f;
+    for (int j = lane; j < n1; j += 32) mx = fmaxf(mx, W.expo(__ldg(W.row + j), j));
+    mx = warp_max(mx);
+    W.shift32 = -mx;
+    W.shift64 = -(double)mx * kLn2d;
+  }
+  // pass A: row total
+  double part = 0.0;  // float64 partial sums: keeps the cdf within ~1e-8 of the float64 reference
+  if (vec) {
+    for (int j = lane * 4; j < n1; j += 128) { const float4 w = W.four(j); part += (double)((w.x + w.y) + (w.z + w.w)); }
+  } else {
+    for (int j = lane; j < n1; j += 32) part += (double)W.one(j);
+  }
+  const double total = warp_sum(part);
+  int jsel = -1;
+  if (!(total > 0.0) || !isfinite(total)) {
+    if (lane == 0 && status) atomicOr(status, CFM_FLAG_NONFINITE);
+    return min(n1 - 1, (int)(frac * (double)n1));
+  }
+  const double target = frac * total;
+  double run = 0.0;
+  // pass B: coarse blocks of 1024 columns, then a fine scan inside the block that crosses
+  for (int b0 = 0; b0 < n1 && jsel < 0; b0 += 1024) {
+    const int bend = min(n1, b0 + 1024);
+    double bp = 0.0;
+    if (vec) {
+      for (int j = b0 + lane * 4; j < bend; j += 128) { const float4 w = W.four(j); bp += (double)((w.x + w.y) + (w.z + w.w)); }
+    } else {
+      for (int j = b0 + lane; j < bend; j += 32) bp += (double)W.one(j);
+    }
+    const double bsum = warp_sum(bp);
+    if (run + bsum > target || bend == n1) {
+      // fine scan: 128 (vec) or 32 (scalar) columns per step, in natural column order
+      const int step = vec ? 128 : 32;
+      for (int j0 = b0; j0 < bend && jsel < 0; j0 += step) {
+        float w[4] = {0.f, 0.f, 0.f, 0.f};
+        const int j = j0 + (vec ? lane * 4 : lane);
+        if (j < bend) {
+          if (vec) { const float4 q = W.four(j); w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w; }
+          else w[0] = W.one(j);
+        }
+        const double mine = (double)((w[0] + w[1]) + (w[2] + w[3]));
+        double incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const bool hit = (j < bend) && (run + incl > target);
+        const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+        if (ballot) {
+          const int src = __ffs(ballot) - 1;
+          // the winning lane resolves the element inside its float4
+          int jj = -1;
+          if (lane == src) {
+            double r2 = run + incl - mine;
+            const int cnt = vec ? 4 : 1;
+            jj = j + cnt - 1;
+            for (int c = 0; c < cnt; ++c) { r2 += (double)w[c]; if (r2 > target) { jj = j + c; break; } }
+          }
+          jsel = __shfl_sync(0xffffffffu, jj, src);
+        }
+        run += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      if (jsel < 0) jsel = bend - 1;  // rounding at the very end of the row
+    } else {
+      run += bsum;
+    }
+  }
+  if (jsel < 0) jsel = n1 - 1;
+  return jsel;
+}
+
 __global__ void draw_uniform_rows_kernel(const float* __restrict__ M, int n0, int n1, int64_t ldm,
                                          float reg, const float* __restrict__ cost_max, int normalize,
-                                         const double* __restrict__ lv, const double* __restrict__ uniforms,
+                                         const double* __restrict__ lu, const double* __restrict__ lv,
+                                         const double* __restrict__ uniforms,
                                          const int64_t* __restrict__ rows, int n_draws,
                                          int64_t* __restrict__ i_out, int64_t* __restrict__ j_out,
                                          int32_t* status) {
@@ -180,91 +290,27 @@ __global__ void draw_uniform_rows_kernel(const float* __restrict__ M, int n0, in
   double frac;
   if (rows != nullptr) {  // row-conditional draw  j ~ pi[i, :] / sum(pi[i, :])  (sample_trajectory, :239-248)
     i = (int)rows[draw];
+    i = min(max(i, 0), n0 - 1);
     frac = u;
   } else {
     i = (int)(u * (double)n0);
     if (i >= n0) i = n0 - 1;
     frac = u * (double)n0 - (double)i;  // position inside row i's cdf cell, in [0, 1)
   }
-  const float scale = normalize ? __ldg(cost_max) : 1.f;
+  const float cmax = cost_max ? __ldg(cost_max) : 1.f;
+  const float scale = normalize ? cmax : 1.f;
   const float c2 = -kLog2e / (reg * scale);
   const float* row = M + (int64_t)i * ldm;
   const bool vec = ((ldm & 3) == 0) && ((n1 & 3) == 0) && ((reinterpret_cast<uintptr_t>(M) & 15) == 0);
-  const float vref = (float)(lv[0] * kLog2ed);
-  auto weight = [&](int j) -> float {
-    return ex2f(fmaf(__ldg(row + j), c2, (float)(lv[j] * kLog2ed) - vref));
-  };
-  auto weight4 = [&](int j) -> float4 {
-    const float4 m = *reinterpret_cast<const float4*>(row + j);
-    return make_float4(ex2f(fmaf(m.x, c2, (float)(lv[j] * kLog2ed) - vref)),
-                       ex2f(fmaf(m.y, c2, (float)(lv[j + 1] * kLog2ed) - vref)),
-                       ex2f(fmaf(m.z, c2, (float)(lv[j + 2] * kLog2ed) - vref)),
-                       ex2f(fmaf(m.w, c2, (float)(lv[j + 3] * kLog2ed) - vref)));
-  };
-  // pass A: row total
-  double part = 0.0;  // float64 partial sums: keeps the cdf within ~1e-8 of the float64 reference
-  if (vec) {
-    for (int j = lane * 4; j < n1; j += 128) { const float4 w = weight4(j); part += (double)((w.x + w.y) + (w.z + w.w)); }
+  // same rule as the solver's auto mode: beyond |M/reg| ~ 64 the exponent needs float64 adds
+  const bool precise = cost_max ? !((normalize ? 1.f : cmax) / reg <= 64.f) : true;
+  int jsel;
+  if (precise) {
+    RowWeight<true> W{row, lv, c2, reg, cmax, normalize, 0.f, lu ? lu[i] : 0.0};
+    jsel = draw_in_row<true>(W, lu != nullptr, n1, vec, frac, lane, status);
   } else {
-    for (int j = lane; j < n1; j += 32) part += (double)weight(j);
-  }
-  const double total = warp_sum(part);
-  int jsel = -1;
-  if (!(total > 0.0) || !isfinite(total)) {
-    if (lane == 0 && status) atomicOr(status, CFM_FLAG_NONFINITE);
-    jsel = min(n1 - 1, (int)(frac * (double)n1));
-  } else {
-    const double target = frac * total;
-    double run = 0.0;
-    // pass B: coarse blocks of 1024 columns, then a fine scan inside the block that crosses
-    for (int b0 = 0; b0 < n1 && jsel < 0; b0 += 1024) {
-      const int bend = min(n1, b0 + 1024);
-      double bp = 0.0;
-      if (vec) {
-        for (int j = b0 + lane * 4; j < bend; j += 128) { const float4 w = weight4(j); bp += (double)((w.x + w.y) + (w.z + w.w)); }
-      } else {
-        for (int j = b0 + lane; j < bend; j += 32) bp += (double)weight(j);
-      }
-      const double bsum = warp_sum(bp);
-      if (run + bsum > target || bend == n1) {
-        // fine scan: 128 (vec) or 32 (scalar) columns per step, in natural column order
-        const int step = vec ? 128 : 32;
-        for (int j0 = b0; j0 < bend && jsel < 0; j0 += step) {
-          float w[4] = {0.f, 0.f, 0.f, 0.f};
-          const int j = j0 + (vec ? lane * 4 : lane);
-          if (j < bend) {
-            if (vec) { const float4 q = weight4(j); w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w; }
-            else w[0] = weight(j);
-          }
-          const double mine = (double)((w[0] + w[1]) + (w[2] + w[3]));
-          double incl = mine;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const double t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-          }
-          const bool hit = (j < bend) && (run + incl > target);
-          const unsigned ballot = __ballot_sync(0xffffffffu, hit);
-          if (ballot) {
-            const int src = __ffs(ballot) - 1;
-            // the winning lane resolves the element inside its float4
-            int jj = -1;
-            if (lane == src) {
-              double r2 = run + incl - mine;
-              const int cnt = vec ? 4 : 1;
-              jj = j + cnt - 1;
-              for (int c = 0; c < cnt; ++c) { r2 += (double)w[c]; if (r2 > target) { jj = j + c; break; } }
-            }
-            jsel = __shfl_sync(0xffffffffu, jj, src);
-          }
-          run += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        if (jsel < 0) jsel = bend - 1;  // rounding at the very end of the row
-      } else {
-        run += bsum;
-      }
-    }
-    if (jsel < 0) jsel = n1 - 1;
+    RowWeight<false> W{row, lv, c2, reg, cmax, normalize, lu ? (float)(lu[i] * kLog2ed) : 0.f, 0.0};
+    jsel = draw_in_row<false>(W, lu != nullptr, n1, vec, frac, lane, status);
   }
   if (lane == 0) {
     if (i_out) i_out[draw] = i;
@@ -284,7 +330,8 @@ __global__ void perm_draw_kernel(const int32_t* __restrict__ sigma, const double
     if (stairs[mid] > u) hi = mid; else lo = mid + 1;
   }
   i_out[d] = lo;
-  j_out[d] = sigma[lo];
+  const int j = sigma[lo];
+  j_out[d] = (j >= 0 && j < n) ? j : lo;  // an infeasible solve leaves rows unassigned (status says so): stay in range
 }
 
 template <class E>
@@ -319,7 +366,7 @@ extern "C" int cfm_plan_sample(const float* M, int n0, int n1, int64_t ldm, floa
   if (uniform_rows) {
     if (n_draws == 0) return CFM_OK;
     draw_uniform_rows_kernel<<<(n_draws + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
-        M, n0, n1, ldm, reg, cost_max, normalize, log_v, uniforms, nullptr, n_draws, i_out, j_out, status); ::cfm::note_launches(1);
+        M, n0, n1, ldm, reg, cost_max, normalize, log_u, log_v, uniforms, nullptr, n_draws, i_out, j_out, status); ::cfm::note_launches(1);
     CFM_CUDA_OK(cudaGetLastError());
     return CFM_OK;
   }
@@ -329,15 +376,15 @@ extern "C" int cfm_plan_sample(const float* M, int n0, int n1, int64_t ldm, floa
 }
 
 extern "C" int cfm_plan_sample_rows(const float* M, int n0, int n1, int64_t ldm, float reg,
-                                    const float* cost_max, int normalize, const double* log_v,
-                                    const int64_t* rows, const double* uniforms, int n_draws,
-                                    int64_t* j_out, int32_t* status, void* stream) {
+                                    const float* cost_max, int normalize, const double* log_u,
+                                    const double* log_v, const int64_t* rows, const double* uniforms,
+                                    int n_draws, int64_t* j_out, int32_t* status, void* stream) {
   CFM_REQUIRE(M && log_v && (n_draws == 0 || (rows && uniforms && j_out)), "cfm_plan_sample_rows: null pointer");
   CFM_REQUIRE(n0 > 0 && n1 > 0 && ldm >= n1 && n_draws >= 0, "cfm_plan_sample_rows: bad shape");
   CFM_REQUIRE(!(normalize && !cost_max), "cfm_plan_sample_rows: normalize needs cost_max");
   if (n_draws == 0) return CFM_OK;
   draw_uniform_rows_kernel<<<(n_draws + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
-      M, n0, n1, ldm, reg, cost_max, normalize, log_v, uniforms, rows, n_draws, nullptr, j_out, status); ::cfm::note_launches(1);
+      M, n0, n1, ldm, reg, cost_max, normalize, log_u, log_v, uniforms, rows, n_draws, nullptr, j_out, status); ::cfm::note_launches(1);
   CFM_CUDA_OK(cudaGetLastError());
   return CFM_OK;
 }

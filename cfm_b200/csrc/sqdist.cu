@@ -4,6 +4,7 @@
 // Two code paths behind cfm_sqdist_f32:
 //   algo 1  SIMT fp32 FMA GEMM (gemm_simt.cuh)      -- any shape / alignment
 //   algo 2  tcgen05 3xTF32 GEMM (sqdist_tc.cu)      -- d % 4 == 0, 16B-aligned rows
+//   algo 3  tcgen05 fp16x3 GEMM (sqdist_h3.cu)      -- same shapes, twice the tensor rate (auto mode's choice)
 // Both share the row-norm pre-pass and the epilogue
 //   M_ij = (sqrt(max(|x0_i|^2 + |x1_j|^2 - 2 <x0_i, x1_j>, 0)))^2
 // which follows ATen's _euclidean_dist (clamp_min(0).sqrt()) and the reference's `** 2`.
@@ -71,6 +72,11 @@ int sqdist_tc_launch(const float* x0, const float* x1, float* M, int n0, int n1,
                      int64_t ldm, int squared, float* cost_max, const float* nx, const float* ny,
                      void* ws, size_t ws_bytes, cudaStream_t s);
 
+// implemented in sqdist_h3.cu (fp16x3 scheme; the pre-pass also writes the row norms)
+size_t sqdist_h3_workspace_bytes(int n0, int n1, int d);
+int sqdist_h3_launch(const float* x0, const float* x1, float* M, int n0, int n1, int d, int64_t ldm, int squared,
+                     float* cost_max, float* nx, float* ny, void* ws, size_t ws_bytes, cudaStream_t s);
+
 static size_t norms_bytes(int n0, int n1) {
   return align_up((size_t)n0 * 4, 256) + align_up((size_t)n1 * 4, 256);
 }
@@ -81,7 +87,8 @@ using namespace cfm;
 
 extern "C" size_t cfm_sqdist_workspace_bytes(int n0, int n1, int d, int algo) {
   size_t b = norms_bytes(n0, n1);
-  if (algo != 1) b += sqdist_tc_workspace_bytes(n0, n1, d);
+  if (algo == 2) b += sqdist_tc_workspace_bytes(n0, n1, d);
+  else if (algo != 1) b += sqdist_h3_workspace_bytes(n0, n1, d);  // auto / 3
   return b;
 }
 
@@ -92,11 +99,13 @@ extern "C" int cfm_sqdist_f32(const float* x0, const float* x1, float* M, int n0
   CFM_REQUIRE(x0 && x1 && M, "cfm_sqdist_f32: null pointer");
   CFM_REQUIRE(n0 > 0 && n1 > 0 && d > 0 && ldm >= n1, "cfm_sqdist_f32: bad shape n0=%d n1=%d d=%d ldm=%lld",
               n0, n1, d, (long long)ldm);
-  CFM_REQUIRE(algo >= 0 && algo <= 2, "cfm_sqdist_f32: unknown algo %d", algo);
+  CFM_REQUIRE(algo >= 0 && algo <= 3, "cfm_sqdist_f32: unknown algo %d", algo);
   const bool tc_ok = sqdist_tc_supported(n0, n1, d, x0, x1, M, ldm) != 0;
-  if (algo == 2) CFM_REQUIRE(tc_ok, "cfm_sqdist_f32: tcgen05 path needs d %% 4 == 0, 16B-aligned x0/x1/M and ldm %% 4 == 0");
-  const bool use_tc = (algo == 2) || (algo == 0 && tc_ok && (int64_t)n0 * n1 >= 256 * 256 && d >= 32);
-  const size_t need = norms_bytes(n0, n1) + (use_tc ? sqdist_tc_workspace_bytes(n0, n1, d) : 0);
+  if (algo >= 2) CFM_REQUIRE(tc_ok, "cfm_sqdist_f32: tcgen05 paths need d %% 4 == 0, 16B-aligned x0/x1/M and ldm %% 4 == 0");
+  const bool use_h3 = (algo == 3) || (algo == 0 && tc_ok && (int64_t)n0 * n1 >= 256 * 256 && d >= 32);
+  const bool use_tc = (algo == 2);
+  const size_t need = norms_bytes(n0, n1) + (use_tc ? sqdist_tc_workspace_bytes(n0, n1, d) : 0) +
+                      (use_h3 ? sqdist_h3_workspace_bytes(n0, n1, d) : 0);
   CFM_REQUIRE(workspace && workspace_bytes >= need, "cfm_sqdist_f32: workspace too small (%zu < %zu)",
               workspace_bytes, need);
   float* nx = reinterpret_cast<float*>(workspace);
@@ -104,6 +113,9 @@ extern "C" int cfm_sqdist_f32(const float* x0, const float* x1, float* M, int n0
   void* tcws = reinterpret_cast<char*>(workspace) + norms_bytes(n0, n1);
 
   if (cost_max) CFM_CUDA_OK(cudaMemsetAsync(cost_max, 0, sizeof(float), s));
+  if (use_h3)  // norms, row scales and the fp16 operand split come from one fused pre-pass per input
+    return sqdist_h3_launch(x0, x1, M, n0, n1, d, ldm, squared, cost_max, nx, ny, tcws,
+                            workspace_bytes - norms_bytes(n0, n1), s);
   row_sqnorm_kernel<<<(n0 + 7) / 8, 256, 0, s>>>(x0, n0, d, nx); ::cfm::note_launches(1);
   row_sqnorm_kernel<<<(n1 + 7) / 8, 256, 0, s>>>(x1, n1, d, ny); ::cfm::note_launches(1);
   CFM_CUDA_OK(cudaGetLastError());

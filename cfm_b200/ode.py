@@ -49,6 +49,12 @@ class NeuralODE(torch.nn.Module):
         self.use_cuda_graph = True  # replay one captured dopri5 step per iteration
         self.max_burst = 32         # steps enqueued between two host reads of the controller state
         self.use_fused_small = True  # small MLPs: the whole trajectory in one launch (csrc/ode_small.cu)
+        # Row-sharded integration across ranks (cfm_b200.dist.sharded_trajectory(..., lockstep=True)): a
+        # torch.distributed group (or True for the default group).  torchdyn's controller uses ONE error norm
+        # over the whole batch; with the batch split over ranks, the per-shard sums of squares (one float64
+        # per step attempt, three more for the initial step) are all-reduced so that every rank takes exactly
+        # the step sequence a single process would take on the full batch.
+        self.lockstep = None
         self._plans = {}
 
     @torch.no_grad()
@@ -65,8 +71,10 @@ class NeuralODE(torch.nn.Module):
         shape = x.shape
         x0 = x.detach().reshape(shape[0], -1).float().contiguous()
         t_span = torch.as_tensor(t_span, dtype=torch.float32)
-        if self.use_fused_small and t_span.numel() >= 2 and _ffi.lib().cfm_ode_small_supported(
-                x0.shape[0], x0.shape[1], mlp.w, mlp.out_dim):
+        if self.lockstep is not None and self.solver != "dopri5":
+            raise NotImplementedError("lock-step sharding applies to the adaptive solver (dopri5)")
+        if self.lockstep is None and self.use_fused_small and t_span.numel() >= 2 \
+                and _ffi.lib().cfm_ode_small_supported(x0.shape[0], x0.shape[1], mlp.w, mlp.out_dim):
             out = self._fused_small(mlp, x0, t_span.to(dev).contiguous())
         elif self.solver == "euler":
             out = self._euler(mlp, x0, t_span)
@@ -139,13 +147,15 @@ class NeuralODE(torch.nn.Module):
                 mlp.vector_field(P["t_stage"], out, out=k[stage])
         _ffi.check(L.cfm_rk_error_norm(stp, _ffi.ptr(x), _ffi.ptr(xnew), _ffi.ptr(k), numel, sp),
                    "cfm_rk_error_norm")
-        _ffi.check(L.cfm_rk_control(stp, _ffi.ptr(P["t_span"]), numel, sp), "cfm_rk_control")
+        if P["group"] is not None:  # lock-step: the error norm is over the rows of ALL ranks
+            P["dist"].all_reduce(P["err_acc"], group=P["group"])
+        _ffi.check(L.cfm_rk_control(stp, _ffi.ptr(P["t_span"]), P["numel_global"], sp), "cfm_rk_control")
         _ffi.check(L.cfm_rk_commit(stp, _ffi.ptr(x), _ffi.ptr(xnew), _ffi.ptr(k), _ffi.ptr(P["traj"]),
                                    numel, sp), "cfm_rk_commit")
 
     def _plan(self, mlp, B, D, n_span, dev):
         """Persistent buffers (+ the captured step graph) for one problem shape and weight version."""
-        key = (id(mlp), B, D, n_span, str(dev), mlp._weights_key(), mlp.mlp_algo, mlp.act)
+        key = (id(mlp), B, D, n_span, str(dev), mlp._weights_key(), mlp.mlp_algo, mlp.act, self.lockstep is not None)
         P = self._plans.get(key)
         if P is not None:
             return P
@@ -161,10 +171,13 @@ class NeuralODE(torch.nn.Module):
              "t_stage": torch.zeros(1, dtype=torch.float32, device=dev),
              "scratch": torch.zeros(4, dtype=torch.float64, device=dev),
              "pinned": torch.empty(ctypes_sizeof_state(), dtype=torch.uint8, pin_memory=True),
-             "xs_hi": None, "xs_lo": None, "graph": None}
+             "xs_hi": None, "xs_lo": None, "graph": None, "group": None, "dist": None, "numel_global": B * D}
+        off = _ffi.RkState.err_acc.offset  # the float64 accumulator inside the device state struct
+        P["err_acc"] = st[off:off + 8].view(torch.float64)
         if mlp.tc_path(B):
-            P["xs_hi"] = torch.empty((B, D), dtype=torch.float32, device=dev)
-            P["xs_lo"] = torch.empty((B, D), dtype=torch.float32, device=dev)
+            # stage inputs go to the MLP as its fp16x3 tensor-core operand pair (hi, lo), written by the RK kernel
+            P["xs_hi"] = torch.empty((B, D), dtype=torch.float16, device=dev)
+            P["xs_lo"] = torch.empty((B, D), dtype=torch.float16, device=dev)
         self._plans[key] = P
         return P
 
@@ -188,15 +201,40 @@ class NeuralODE(torch.nn.Module):
         st_host.n_span, st_host.ckpt, st_host.save_slot = n_span, 1, -1
         st.copy_(torch.frombuffer(bytearray(bytes(st_host)), dtype=torch.uint8), non_blocking=False)
 
+        lock = self.lockstep is not None
+        if lock:
+            import torch.distributed as tdist
+            P["dist"] = tdist
+            P["group"] = None if self.lockstep is True else self.lockstep
+            if not (tdist.is_available() and tdist.is_initialized()):
+                raise RuntimeError("NeuralODE.lockstep needs an initialised torch.distributed process group")
+            cnt = torch.tensor([numel], dtype=torch.int64, device=dev)
+            tdist.all_reduce(cnt, group=P["group"])
+            P["numel_global"] = int(cnt.item())
+            P["group"] = P["group"] if P["group"] is not None else tdist.group.WORLD
+        else:
+            P["group"], P["numel_global"] = None, numel
+        ng = P["numel_global"]
+
         # k1 = f(t0, x); Hairer initial step needs one extra evaluation
         mlp.vector_field(st_host.t, x, out=k[0])
-        _ffi.check(L.cfm_rk_init_a(stp, _ffi.ptr(x), _ffi.ptr(k[0]), _ffi.ptr(xs), _ffi.ptr(P["t_stage"]),
-                                   _ffi.ptr(P["scratch"]), numel, sp), "cfm_rk_init_a")
+        _ffi.check(L.cfm_rk_init_sums(stp, _ffi.ptr(x), _ffi.ptr(k[0]), None, _ffi.ptr(P["scratch"]), numel, 0, sp),
+                   "cfm_rk_init_sums")
+        if lock:
+            P["dist"].all_reduce(P["scratch"], group=P["group"])
+        _ffi.check(L.cfm_rk_init_probe(stp, _ffi.ptr(x), _ffi.ptr(k[0]), _ffi.ptr(xs), _ffi.ptr(P["t_stage"]),
+                                       _ffi.ptr(P["scratch"]), numel, ng, sp), "cfm_rk_init_probe")
         mlp.vector_field(P["t_stage"], xs, out=k[1])
-        _ffi.check(L.cfm_rk_init_b(stp, _ffi.ptr(x), _ffi.ptr(k[0]), _ffi.ptr(k[1]), _ffi.ptr(P["t_span"]),
-                                   _ffi.ptr(P["scratch"]), numel, sp), "cfm_rk_init_b")
+        if lock:  # phase 1 adds into scratch[2] only; keep the already-global scratch[0:2] out of the second reduce
+            P["scratch"][2:].zero_()
+        _ffi.check(L.cfm_rk_init_sums(stp, _ffi.ptr(x), _ffi.ptr(k[0]), _ffi.ptr(k[1]), _ffi.ptr(P["scratch"]),
+                                      numel, 1, sp), "cfm_rk_init_sums")
+        if lock:
+            P["dist"].all_reduce(P["scratch"][2:3], group=P["group"])
+        _ffi.check(L.cfm_rk_init_finish(stp, _ffi.ptr(P["t_span"]), _ffi.ptr(P["scratch"]), ng, sp),
+                   "cfm_rk_init_finish")
 
-        if self.use_cuda_graph and P["graph"] is None:
+        if self.use_cuda_graph and not lock and P["graph"] is None:
             # the step is a fixed kernel sequence whose control flow lives in device memory: capture it
             # once (the eager init above has already loaded every kernel) and replay it per step
             g = torch.cuda.CUDAGraph()
@@ -215,7 +253,7 @@ class NeuralODE(torch.nn.Module):
             # device (done flag), so the bound only has to be safe, not tight.
             burst = max(1, min(self.max_burst, n_span - int(cur.ckpt)))
             for _ in range(burst):
-                if P["graph"] is not None:
+                if P["graph"] is not None and not lock:
                     P["graph"].replay()
                 else:
                     self._enqueue_step(mlp, P)
@@ -228,7 +266,8 @@ class NeuralODE(torch.nn.Module):
         else:
             raise RuntimeError("dopri5: step budget exhausted")
         self.stats = {"nfe": cur.nfe, "accepted": cur.accepted, "rejected": cur.rejected,
-                      "t": cur.t, "last_ratio": cur.ratio, "graph": P["graph"] is not None}
+                      "t": cur.t, "last_ratio": cur.ratio, "graph": P["graph"] is not None and not lock,
+                      "lockstep": lock}
         return traj.clone()
 
 

@@ -14,6 +14,7 @@ cdf; here the same ``np.random.random_sample(size)`` values are drawn on the hos
 inversion runs on the device, so reseeding ``np.random`` reproduces a draw just as in the
 reference.
 """
+import collections
 import ctypes as C
 import math
 import warnings
@@ -54,9 +55,19 @@ def _pick_device(*tensors):
 
 
 class _Coupling:
-    """Device-side result of one solve: cost matrix + either potentials or a permutation."""
+    """Device-side result of one solve: cost matrix + either potentials or a permutation.  For exact OT
+    between batches of different sizes (``expand`` = (m0, m1, L)) sigma is the assignment of the
+    L x L replicated problem, L = lcm(n0, n1): row a stands for source a // m0, column b for target
+    b // m1, every pair carries mass 1 / L."""
     __slots__ = ("M", "cost_max", "n0", "n1", "log_u", "log_v", "sigma", "status", "err",
-                 "total_cost", "reg", "normalize", "method", "x0_dev", "x1_dev")
+                 "total_cost", "reg", "normalize", "method", "x0_dev", "x1_dev", "expand")
+
+
+# Rectangular exact OT is solved as an assignment problem of size lcm(n0, n1); beyond this size the
+# replicated cost matrix stops being a sensible use of the exact solver (O(L^3) worst case)
+_MAX_EXPANDED = 8192
+# pinned staging slots for the uniforms of the pair draw (see OTPlanSampler._uniforms)
+_U_RING = 4
 
 
 class _StageTimer:
@@ -127,8 +138,61 @@ class OTPlanSampler:
         self.precision = precision
         self.stall_tol = float(stall_tol)
         self.cost_algo = int(cost_algo)
-        self.last_info = {}
+        self._last_info = {}
+        self._pending = collections.deque()  # deferred status words of warn=False calls (event, pinned, coupling)
+        self._bufs = collections.OrderedDict()  # (n0, n1, d, device, stream) -> preallocated device buffers
+        self._u_ring = {}                       # (n, device) -> pinned uniform staging ring
         self.stage_events = None  # set to a list to collect (stage, start_event, end_event)
+
+    # ------------------------------------------------------------------ status words
+    @property
+    def last_info(self):
+        """Diagnostics of the most recent solve ({"flags", "iterations", ...}); resolves (synchronises on)
+        any status word a ``warn=False`` call left pending."""
+        self._flush_pending(block=True)
+        return self._last_info
+
+    @last_info.setter
+    def last_info(self, value):
+        self._last_info = value
+
+    def _flush_pending(self, block=False):
+        """Evaluate status words whose device->host copy has landed (all of them when ``block``)."""
+        while self._pending:
+            ev, pinned, cp = self._pending[0]
+            if not block and not ev.query():
+                break
+            ev.synchronize()
+            self._pending.popleft()
+            self._evaluate_status(cp, pinned.tolist(), None)
+
+    def _buffers(self, n0, n1, d, device, algo):
+        """Device buffers of one problem shape, allocated once per (shape, device, stream) and reused by every
+        later call on that stream: the cost matrix, the kernels' workspaces, the potentials and the draw's
+        index / uniform arrays.  A training loop therefore makes no allocator call (and no cudaMalloc, which
+        synchronises the device) in steady state.  Stream-ordered reuse is safe because every consumer of
+        a call's buffers is enqueued on the same stream before the next call's producers."""
+        L = _ffi.lib()
+        stream = torch.cuda.current_stream(device).cuda_stream
+        key = (n0, n1, d, str(device), stream, algo, self.method)
+        B = self._bufs.get(key)
+        if B is not None:
+            self._bufs.move_to_end(key)
+            return B
+        ld = (n1 + 3) // 4 * 4  # 16-byte aligned rows for the float4 / TMA paths
+        B = {"ld": ld,
+             "M": torch.empty((n0, ld), dtype=torch.float32, device=device),
+             "cmax": torch.empty(1, dtype=torch.float32, device=device),
+             "ws_cost": _ffi.workspace(L.cfm_sqdist_workspace_bytes(n0, n1, d, algo), device)}
+        if self.method == "sinkhorn":
+            B["log_u"] = torch.empty(n0, dtype=torch.float64, device=device)
+            B["log_v"] = torch.empty(n1, dtype=torch.float64, device=device)
+            B["ws_sk"] = _ffi.workspace(L.cfm_sinkhorn_workspace_bytes(n0, n1), device)
+            B["ws_draw"] = _ffi.workspace(L.cfm_plan_sample_workspace_bytes(n0), device)
+        self._bufs[key] = B
+        while len(self._bufs) > 2:  # keep the two most recent shapes (e.g. a ragged last batch)
+            self._bufs.popitem(last=False)
+        return B
 
     def _timed(self, stage, device):
         """Context manager recording CUDA events around a stage when profiling is on."""
@@ -143,61 +207,92 @@ class OTPlanSampler:
             raise RuntimeError(f"X1 and X2 must have the same number of columns. "
                                f"X1: {a.shape[1]} X2: {b.shape[1]}")
         n0, n1, d = a.shape[0], b.shape[0], a.shape[1]
-        ld = (n1 + 3) // 4 * 4  # 16-byte aligned rows for the float4 / TMA paths
-        Mbuf = torch.empty((n0, ld), dtype=torch.float32, device=device)
-        cmax = torch.empty(1, dtype=torch.float32, device=device)
         # exact OT needs fp32-FMA-grade costs (sigma must not flip): SIMT path unless overridden;
-        # the tcgen05 3xTF32 path (~1e-6 relative, truncating accumulator) serves Sinkhorn
+        # the tensor-core paths (~1e-6 relative, truncating accumulator) serve Sinkhorn
         algo = self.cost_algo if self.cost_algo else (1 if self.method == "exact" else 0)
-        ws = _ffi.workspace(L.cfm_sqdist_workspace_bytes(n0, n1, d, algo), device)
-        _ffi.check(L.cfm_sqdist_f32(_ffi.ptr(a), _ffi.ptr(b), _ffi.ptr(Mbuf), n0, n1, d, ld,
-                                    1 if squared else 0, _ffi.ptr(cmax), algo,
-                                    _ffi.ptr(ws), ws.numel(), _ffi.stream_ptr(device)),
-                   "cfm_sqdist_f32")
+        B = self._buffers(n0, n1, d, device, algo)
+        Mbuf, cmax, ws = B["M"], B["cmax"], B["ws_cost"]
+        with torch.cuda.device(device):
+            _ffi.check(L.cfm_sqdist_f32(_ffi.ptr(a), _ffi.ptr(b), _ffi.ptr(Mbuf), n0, n1, d, B["ld"],
+                                        1 if squared else 0, _ffi.ptr(cmax), algo,
+                                        _ffi.ptr(ws), ws.numel(), _ffi.stream_ptr(device)),
+                       "cfm_sqdist_f32")
         self._last_inputs = (a, b)
+        self._last_bufs = B
         return Mbuf, cmax, n0, n1
 
     def _solve_sinkhorn(self, Mbuf, cmax, n0, n1, reg, normalize, num_iter_max=None,
-                        stop_thr=None):
+                        stop_thr=None, bufs=None):
         L = _ffi.lib()
         dev = Mbuf.device
         cp = _Coupling()
         cp.M, cp.cost_max, cp.n0, cp.n1, cp.reg, cp.normalize = Mbuf, cmax, n0, n1, float(reg), bool(normalize)
-        cp.method, cp.sigma, cp.total_cost = "sinkhorn", None, None
-        cp.log_u = torch.empty(n0, dtype=torch.float64, device=dev)
-        cp.log_v = torch.empty(n1, dtype=torch.float64, device=dev)
+        cp.method, cp.sigma, cp.total_cost, cp.expand = "sinkhorn", None, None, None
+        if bufs is not None and "log_u" in bufs:  # preallocated per shape (see _buffers)
+            cp.log_u, cp.log_v, ws = bufs["log_u"], bufs["log_v"], bufs["ws_sk"]
+        else:
+            cp.log_u = torch.empty(n0, dtype=torch.float64, device=dev)
+            cp.log_v = torch.empty(n1, dtype=torch.float64, device=dev)
+            ws = _ffi.workspace(L.cfm_sinkhorn_workspace_bytes(n0, n1), dev)
+        # the status word and the error are per call: a deferred report may read them after later solves
         cp.status = torch.zeros(4, dtype=torch.int32, device=dev)
         cp.err = torch.zeros(1, dtype=torch.float64, device=dev)
-        ws = _ffi.workspace(L.cfm_sinkhorn_workspace_bytes(n0, n1), dev)
         prec = {"auto": -1, "fp32": 0, "fp64": 1, "fp32-generic": 2, "fp64-mixed": 3}[self.precision]
-        _ffi.check(L.cfm_sinkhorn_log_f32(
-            _ffi.ptr(Mbuf), n0, n1, Mbuf.stride(0), float(reg), _ffi.ptr(cmax), int(bool(normalize)),
-            int(self.num_iter_max if num_iter_max is None else num_iter_max),
-            float(self.stop_thr if stop_thr is None else stop_thr), 10, prec,
-            0.0 if (self.stop_thr if stop_thr is None else stop_thr) <= 0 else self.stall_tol,
-            _ffi.ptr(cp.log_u), _ffi.ptr(cp.log_v), _ffi.ptr(cp.status), _ffi.ptr(cp.err),
-            _ffi.ptr(ws), ws.numel(), _ffi.stream_ptr(dev)), "cfm_sinkhorn_log_f32")
+        with torch.cuda.device(dev):
+            _ffi.check(L.cfm_sinkhorn_log_f32(
+                _ffi.ptr(Mbuf), n0, n1, Mbuf.stride(0), float(reg), _ffi.ptr(cmax), int(bool(normalize)),
+                int(self.num_iter_max if num_iter_max is None else num_iter_max),
+                float(self.stop_thr if stop_thr is None else stop_thr), 10, prec,
+                0.0 if (self.stop_thr if stop_thr is None else stop_thr) <= 0 else self.stall_tol,
+                _ffi.ptr(cp.log_u), _ffi.ptr(cp.log_v), _ffi.ptr(cp.status), _ffi.ptr(cp.err),
+                _ffi.ptr(ws), ws.numel(), _ffi.stream_ptr(dev)), "cfm_sinkhorn_log_f32")
         return cp
 
     def _solve_exact(self, Mbuf, cmax, n0, n1, normalize):
-        if n0 != n1:
-            raise NotImplementedError(
-                "exact OT on the device is implemented for equal batch sizes (the LP optimum is "
-                f"then a permutation); got {n0} and {n1}")
+        """Optimal assignment on the device.  n0 == n1: the LP vertex of uniform marginals is P_sigma / n.
+        n0 != n1 (pot.emd takes any pair of marginals, reference :79,87): the transport polytope with
+        marginals 1/n0, 1/n1 has vertices whose entries are multiples of 1/L, L = lcm(n0, n1), so the LP
+        optimum is the optimal assignment of the L x L problem in which source i is replicated L/n0 times
+        and target j L/n1 times -- solved by the same kernel on the replicated cost matrix."""
         L = _ffi.lib()
         dev = Mbuf.device
         cp = _Coupling()
         cp.M, cp.cost_max, cp.n0, cp.n1, cp.reg, cp.normalize = Mbuf, cmax, n0, n1, None, bool(normalize)
-        cp.method, cp.log_u, cp.log_v, cp.err = "exact", None, None, None
-        cp.sigma = torch.empty(n0, dtype=torch.int32, device=dev)
+        cp.method, cp.log_u, cp.log_v, cp.err, cp.expand = "exact", None, None, None, None
+        n, Msolve = n0, Mbuf
+        if n0 != n1:
+            g = math.gcd(n0, n1)
+            m0, m1 = n1 // g, n0 // g
+            n = n0 * m0
+            if n > _MAX_EXPANDED:
+                raise NotImplementedError(
+                    f"exact OT between batches of {n0} and {n1} samples needs an assignment problem of size "
+                    f"lcm = {n} > {_MAX_EXPANDED}; use equal batch sizes (or sizes with a small lcm)")
+            cp.expand = (m0, m1, n)
+            ld = (n + 3) // 4 * 4
+            Msolve = torch.zeros((n, ld), dtype=torch.float32, device=dev)
+            Msolve[:, :n] = Mbuf[:, :n1].repeat_interleave(m0, dim=0).repeat_interleave(m1, dim=1)
+        cp.sigma = torch.empty(n, dtype=torch.int32, device=dev)
         cp.total_cost = torch.zeros(1, dtype=torch.float64, device=dev)
         cp.status = torch.zeros(4, dtype=torch.int32, device=dev)
-        ws = _ffi.workspace(L.cfm_assign_workspace_bytes(n0), dev)
-        _ffi.check(L.cfm_assign_exact_f32(
-            _ffi.ptr(Mbuf), n0, Mbuf.stride(0), _ffi.ptr(cmax), int(bool(normalize)),
-            _ffi.ptr(cp.sigma), _ffi.ptr(cp.total_cost), _ffi.ptr(cp.status), _ffi.ptr(ws),
-            ws.numel(), _ffi.stream_ptr(dev)), "cfm_assign_exact_f32")
+        ws = _ffi.workspace(L.cfm_assign_workspace_bytes(n), dev)
+        with torch.cuda.device(dev):
+            _ffi.check(L.cfm_assign_exact_f32(
+                _ffi.ptr(Msolve), n, Msolve.stride(0), _ffi.ptr(cmax), int(bool(normalize)),
+                _ffi.ptr(cp.sigma), _ffi.ptr(cp.total_cost), _ffi.ptr(cp.status), _ffi.ptr(ws),
+                ws.numel(), _ffi.stream_ptr(dev)), "cfm_assign_exact_f32")
         return cp
+
+    def _exact_plan(self, cp):
+        """float64 host plan of an exact coupling, the array pot.emd returns (reference :87)."""
+        sigma = cp.sigma.cpu().numpy().astype(np.int64)
+        p = np.zeros((cp.n0, cp.n1), dtype=np.float64)
+        if cp.expand is None:
+            p[np.arange(cp.n0), sigma] = 1.0 / cp.n0
+        else:
+            m0, m1, n = cp.expand
+            np.add.at(p, (np.arange(n) // m0, sigma // m1), 1.0 / n)
+        return p
 
     def _couple(self, x0, x1, device):
         """cost + solve on the device; nothing is synchronised or copied to the host."""
@@ -208,7 +303,8 @@ class OTPlanSampler:
                 cp = self._solve_exact(Mbuf, cmax, n0, n1, self.normalize_cost)
         elif self.method == "sinkhorn":
             with self._timed("solve", device):
-                cp = self._solve_sinkhorn(Mbuf, cmax, n0, n1, self.reg, self.normalize_cost)
+                cp = self._solve_sinkhorn(Mbuf, cmax, n0, n1, self.reg, self.normalize_cost,
+                                          bufs=self._last_bufs)
         else:
             self._ot_fn_unsupported(None, None, None, method=self.method)
         cp.x0_dev, cp.x1_dev = self._last_inputs  # device fp32 copies made for the cost kernel
@@ -226,43 +322,86 @@ class OTPlanSampler:
             st = cache[(n, dev)] = torch.from_numpy(stairs).to(dev)
         return st
 
+    def _uniforms(self, n, dev):
+        """n uniforms of the global NumPy stream (what np.random.choice consumes at :118) on the device,
+        staged through a ring of pinned host slots: a pageable source would make the copy synchronous and
+        drain the launch queue on every call (the host could then never run ahead of the GPU).  A slot is
+        rewritten only after the copy that last read it has completed (event; normally long done)."""
+        key = (n, str(dev))
+        ring = self._u_ring.get(key)
+        if ring is None:
+            ring = self._u_ring[key] = {"k": 0,
+                                        "pin": [torch.empty(n, dtype=torch.float64, pin_memory=True)
+                                                for _ in range(_U_RING)],
+                                        "ev": [None] * _U_RING}
+            if len(self._u_ring) > 4:
+                self._u_ring.pop(next(iter(self._u_ring)))
+        k = ring["k"]
+        ring["k"] = (k + 1) % _U_RING
+        if ring["ev"][k] is not None:
+            ring["ev"][k].synchronize()
+        pin = ring["pin"][k]
+        pin.numpy()[:] = np.random.random_sample(n)
+        u = torch.empty(n, dtype=torch.float64, device=dev)
+        u.copy_(pin, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        ring["ev"][k] = ev
+        return u
+
     def _draw(self, cp, batch_size, u=None):
         """(a6) inverse-cdf draw on the device from host uniforms of the global NumPy RNG (``u``: those
         uniforms already on the device, float64)."""
         L = _ffi.lib()
         dev = cp.M.device
         if u is None:
-            u_host = np.random.random_sample(batch_size)  # the stream np.random.choice consumes (:118)
-            u = torch.from_numpy(u_host).to(dev, non_blocking=True)
+            u = self._uniforms(batch_size, dev)
         i = torch.empty(batch_size, dtype=torch.int64, device=dev)
         j = torch.empty(batch_size, dtype=torch.int64, device=dev)
-        if cp.method == "exact":
-            n = cp.n0
-            st = self._stairs(n, dev)
-            _ffi.check(L.cfm_perm_plan_sample(_ffi.ptr(cp.sigma), _ffi.ptr(st), n, _ffi.ptr(u),
-                                              batch_size, _ffi.ptr(i), _ffi.ptr(j),
-                                              _ffi.stream_ptr(dev)), "cfm_perm_plan_sample")
-        else:
-            ws = _ffi.workspace(L.cfm_plan_sample_workspace_bytes(cp.n0), dev)
-            _ffi.check(L.cfm_plan_sample(
-                _ffi.ptr(cp.M), cp.n0, cp.n1, cp.M.stride(0), cp.reg, _ffi.ptr(cp.cost_max),
-                int(cp.normalize), _ffi.ptr(cp.log_u), _ffi.ptr(cp.log_v), 1, _ffi.ptr(u), batch_size,
-                _ffi.ptr(i), _ffi.ptr(j), _ffi.ptr(cp.status), _ffi.ptr(ws), ws.numel(),
-                _ffi.stream_ptr(dev)), "cfm_plan_sample")
+        with torch.cuda.device(dev):
+            if cp.method == "exact":
+                n = cp.n0
+                st = self._stairs(n, dev)
+                _ffi.check(L.cfm_perm_plan_sample(_ffi.ptr(cp.sigma), _ffi.ptr(st), n, _ffi.ptr(u),
+                                                  batch_size, _ffi.ptr(i), _ffi.ptr(j),
+                                                  _ffi.stream_ptr(dev)), "cfm_perm_plan_sample")
+            else:
+                ws = _ffi.workspace(L.cfm_plan_sample_workspace_bytes(cp.n0), dev)
+                _ffi.check(L.cfm_plan_sample(
+                    _ffi.ptr(cp.M), cp.n0, cp.n1, cp.M.stride(0), cp.reg, _ffi.ptr(cp.cost_max),
+                    int(cp.normalize), _ffi.ptr(cp.log_u), _ffi.ptr(cp.log_v), 1, _ffi.ptr(u), batch_size,
+                    _ffi.ptr(i), _ffi.ptr(j), _ffi.ptr(cp.status), _ffi.ptr(ws), ws.numel(),
+                    _ffi.stream_ptr(dev)), "cfm_plan_sample")
         return i, j
 
-    def _report(self, cp):
-        """Numerical guards of get_map (:88-96) + POT's non-convergence warning; one sync."""
+    def _report(self, cp, defer=False):
+        """Numerical guards of get_map (:88-96) + POT's non-convergence warning.  The status word is ALWAYS
+        evaluated (the reference's ``warn`` only gates the warnings.warn calls): immediately -- one small
+        sync -- or, for ``defer`` (Sinkhorn calls of a warn=False sampler, whose conditions only print),
+        once its copy to pinned memory has landed: at the next call or when ``last_info`` is read."""
+        if defer:
+            pinned = torch.empty(4, dtype=torch.int32, pin_memory=True)
+            pinned.copy_(cp.status, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(cp.status.device))
+            self._pending.append((ev, pinned, cp))
+            while len(self._pending) > 8:
+                self._flush_pending(block=True)
+            return None
+        self._flush_pending(block=True)
         st = cp.status.cpu().tolist()
+        return self._evaluate_status(cp, st, float(cp.err.item()) if cp.err is not None else None)
+
+    def _evaluate_status(self, cp, st, err):
         if cp.method == "exact":  # status = {flags, augmentations, Dijkstra steps, -}
             info = {"flags": st[0], "iterations": st[1], "dijkstra_steps": st[2], "precise": True, "method": cp.method}
         else:                     # status = {flags, iterations, arithmetic, kernel variant}
             info = {"flags": st[0], "iterations": st[1], "precise": bool(st[2]),
                     "arithmetic": ("fp32", "fp64", "fp64-mixed")[st[2]] if 0 <= st[2] <= 2 else st[2],
                     "method": cp.method}
-        if cp.err is not None:
-            info["err"] = float(cp.err.item())
-        self.last_info = info
+        if err is not None:
+            info["err"] = err
+        self._last_info = info
         if st[0] & _ffi.FLAG_INFEASIBLE:
             raise RuntimeError("exact OT: the cost matrix has no finite assignment (inf/nan costs)")
         if st[0] & _ffi.FLAG_NONFINITE:
@@ -286,9 +425,10 @@ class OTPlanSampler:
         if out is None:
             out = torch.empty((idx_dev.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
         row = int(np.prod(x.shape[1:])) if x.dim() > 1 else 1
-        _ffi.check(L.cfm_gather_rows(_ffi.ptr(x), row, x.dtype.itemsize, _ffi.ptr(idx_dev),
-                                     idx_dev.shape[0], _ffi.ptr(out), _ffi.stream_ptr(x.device)),
-                   "cfm_gather_rows")
+        with torch.cuda.device(x.device):  # kernels launch on the CURRENT device: make it the tensors' one
+            _ffi.check(L.cfm_gather_rows(_ffi.ptr(x), row, x.dtype.itemsize, _ffi.ptr(idx_dev),
+                                         idx_dev.shape[0], _ffi.ptr(out), _ffi.stream_ptr(x.device)),
+                       "cfm_gather_rows")
         return out
 
     def _gather_like_input(self, x, x_dev_f32, idx_dev):
@@ -311,10 +451,7 @@ class OTPlanSampler:
         cp = self._couple(x0, x1, device)
         if cp.method == "exact":
             self._report(cp)
-            sigma = cp.sigma.cpu().numpy()
-            p = np.zeros((cp.n0, cp.n1), dtype=np.float64)
-            p[np.arange(cp.n0), sigma] = 1.0 / cp.n0
-            return p
+            return self._exact_plan(cp)
         L = _ffi.lib()
         plan = torch.empty((cp.n0, cp.n1), dtype=torch.float64, device=device)
         mass = torch.zeros(1, dtype=torch.float64, device=device)
@@ -355,23 +492,36 @@ class OTPlanSampler:
         choices = np.random.choice(pi.shape[0] * pi.shape[1], p=p, size=batch_size, replace=replace)
         return np.divmod(choices, pi.shape[1])
 
+    def _finish(self, cp):
+        """Evaluate the solve's status word: at once (exact OT may have to raise; warn=True samplers warn
+        inside the call like the reference) or deferred (Sinkhorn with warn=False: nothing to raise)."""
+        return self._report(cp, defer=(cp.method == "sinkhorn" and not self.warn))
+
+    def _rectangular(self, x0, x1):
+        return self.method == "exact" and x0.shape[0] != x1.shape[0]
+
     def sample_pairs(self, x0, x1, batch_size=None):
         """Device-resident (i, j) int64 index tensors of one coupling (no plan materialised)."""
+        self._flush_pending()
         device = _pick_device(x0, x1)
+        nd = x0.shape[0] if batch_size is None else batch_size
+        if self._rectangular(x0, x1):  # plan is not a permutation: the reference's own host draw on it
+            i, j = self.sample_map(self.get_map(x0, x1), nd)
+            return torch.from_numpy(i).to(device), torch.from_numpy(j).to(device)
         cp = self._couple(x0, x1, device)
-        i, j = self._draw(cp, x0.shape[0] if batch_size is None else batch_size)
-        if self.warn:
-            self._report(cp)
+        i, j = self._draw(cp, nd)
+        self._finish(cp)
         return i, j
 
     def sample_plan(self, x0, x1, replace=True):
         r"""Compute the OT plan $\pi$ between a source and a target minibatch and draw source
         and target samples from pi $(x,z) \sim \pi$ (reference :123-145).  Returns
         ``x0[i], x1[j]`` on the inputs' device."""
-        if not replace:
+        if not replace or self._rectangular(x0, x1):
             pi = self.get_map(x0, x1)
-            i, j = self.sample_map(pi, x0.shape[0], replace=False)
+            i, j = self.sample_map(pi, x0.shape[0], replace=replace)
             return x0[i], x1[j]
+        self._flush_pending()
         device = _pick_device(x0, x1)
         cp = self._couple(x0, x1, device)
         with self._timed("draw", device):
@@ -379,8 +529,7 @@ class OTPlanSampler:
         with self._timed("gather", device):
             out0 = self._gather_like_input(x0, cp.x0_dev, i)
             out1 = self._gather_like_input(x1, cp.x1_dev, j)
-        if self.warn:
-            self._report(cp)
+        self._finish(cp)
         return out0, out1
 
     def sample_plan_with_scipy(self, x0, x1):
@@ -388,6 +537,9 @@ class OTPlanSampler:
         returns x1 permuted by the optimal assignment -- here from the device exact solver."""
         device = _pick_device(x0, x1)
         x0f, x1f = _flat2d(x0), _flat2d(x1)
+        if x0f.shape[0] != x1f.shape[0]:
+            raise ValueError("sample_plan_with_scipy pairs every x0 with one x1: batch sizes must match "
+                             f"(got {x0f.shape[0]} and {x1f.shape[0]})")
         Mbuf, cmax, n0, n1 = self._cost(x0f, x1f, device)
         cp = self._solve_exact(Mbuf, cmax, n0, n1, self.normalize_cost)
         self._report(cp)
@@ -395,10 +547,11 @@ class OTPlanSampler:
 
     def sample_plan_with_labels(self, x0, x1, y0=None, y1=None, replace=True):
         r"""sample_plan that also carries labels through the draw (reference :184-219)."""
-        if not replace:
+        if not replace or self._rectangular(x0, x1):
             pi = self.get_map(x0, x1)
-            i, j = self.sample_map(pi, x0.shape[0], replace=False)
+            i, j = self.sample_map(pi, x0.shape[0], replace=replace)
             return x0[i], x1[j], (y0[i] if y0 is not None else None), (y1[j] if y1 is not None else None)
+        self._flush_pending()
         device = _pick_device(x0, x1)
         cp = self._couple(x0, x1, device)
         i, j = self._draw(cp, x0.shape[0])
@@ -406,18 +559,19 @@ class OTPlanSampler:
                self._gather_like_input(x1, cp.x1_dev, j),
                self._gather(y0, i) if y0 is not None else None,
                self._gather(y1, j) if y1 is not None else None)
-        if self.warn:
-            self._report(cp)
+        self._finish(cp)
         return out
 
     def _draw_rows(self, cp, rows, u):
         """Row-conditional draw  j_k ~ pi[rows[k], :] / sum(pi[rows[k], :])  from device uniforms u."""
         if cp.method == "exact":
-            return cp.sigma.to(torch.int64)[rows]  # one-hot rows: the draw is sigma[i] whatever u is
+            # one-hot rows: the draw is sigma[i] whatever u is (clamped: an infeasible solve raises in
+            # _report right after, but its sigma must not index out of range before that)
+            return cp.sigma.to(torch.int64)[rows].clamp_(0, cp.n1 - 1)
         nxt = torch.empty(rows.shape[0], dtype=torch.int64, device=rows.device)
         _ffi.check(_ffi.lib().cfm_plan_sample_rows(
             _ffi.ptr(cp.M), cp.n0, cp.n1, cp.M.stride(0), cp.reg, _ffi.ptr(cp.cost_max),
-            int(cp.normalize), _ffi.ptr(cp.log_v), _ffi.ptr(rows), _ffi.ptr(u), rows.shape[0],
+            int(cp.normalize), _ffi.ptr(cp.log_u), _ffi.ptr(cp.log_v), _ffi.ptr(rows), _ffi.ptr(u), rows.shape[0],
             _ffi.ptr(nxt), _ffi.ptr(cp.status), _ffi.stream_ptr(rows.device)), "cfm_plan_sample_rows")
         return nxt
 
@@ -439,10 +593,9 @@ class OTPlanSampler:
         # matrix resident at a time
         for t in range(times - 1):
             cp = self._couple(X[:, t], X[:, t + 1], device)
-            u = torch.from_numpy(np.random.random_sample(n)).to(device)
+            u = self._uniforms(n, device)
             nxt = self._draw_rows(cp, rows, u)
-            if self.warn:
-                self._report(cp)
+            self._finish(cp)
             rows = nxt
             chain.append(rows)
             del cp
@@ -475,9 +628,7 @@ class OTPlanSampler:
         Mbuf, cmax, n0, n1 = self._upload_cost(M)
         cp = self._solve_exact(Mbuf, cmax, n0, n1, False)
         self._report(cp)
-        p = np.zeros((n0, n1), dtype=np.float64)
-        p[np.arange(n0), cp.sigma.cpu().numpy()] = 1.0 / n0
-        return p
+        return self._exact_plan(cp)
 
     def _ot_fn_sinkhorn(self, a, b, M, reg):
         """(a, b, M) -> float64 plan, the signature of pot.sinkhorn as bound at reference :51."""
@@ -525,9 +676,9 @@ def wasserstein(
     if kind == "exact":
         cp = s._solve_exact(Mbuf, cmax, n0, n1, False)
         s._report(cp)
-        ret = float(cp.total_cost.item()) / n0
+        ret = float(cp.total_cost.item()) / (n0 if cp.expand is None else cp.expand[2])
     else:
-        cp = s._solve_sinkhorn(Mbuf, cmax, n0, n1, reg, False)
+        cp = s._solve_sinkhorn(Mbuf, cmax, n0, n1, reg, False, bufs=s._last_bufs)
         out = torch.zeros(1, dtype=torch.float64, device=device)
         _ffi.check(_ffi.lib().cfm_plan_dot_cost(
             _ffi.ptr(cp.M), n0, n1, cp.M.stride(0), cp.reg, _ffi.ptr(cp.cost_max), 0,
@@ -641,8 +792,7 @@ class CouplingStream:
     def _wait_oldest(self):
         done, h0, h1, cp = self._inflight.pop(0)
         done.synchronize()
-        if self.sampler.warn:
-            self.sampler._report(cp)
+        self.sampler._report(cp)  # the batch has completed: reading its status word costs no wait
         return h0, h1
 
     def pending(self):

@@ -52,7 +52,9 @@ long long cfm_launch_count(void);
  * un-squared distance otherwise (wasserstein power=1, :297).
  * cost_max (nullable, 1 float): receives max_ij M_ij (the M.max() of :86); must be
  * zeroed by the caller... it is zeroed by this call.
- * algo: 0 auto, 1 SIMT fp32 FMA, 2 tcgen05 3xTF32 (error-compensated, fp32-grade).
+ * algo: 0 auto, 1 SIMT fp32 FMA, 2 tcgen05 3xTF32 (error-compensated, fp32-grade), 3 tcgen05 fp16x3
+ * (x = hi + lo 2^-11 in fp16, three kind::f16 MMAs into two accumulators; same fp32-grade accuracy at twice
+ * the tensor rate and half the operand bytes; what auto picks for aligned shapes).
  */
 size_t cfm_sqdist_workspace_bytes(int n0, int n1, int d, int algo);
 int cfm_sqdist_f32(const float* x0, const float* x1, float* M, int n0, int n1, int d,
@@ -114,7 +116,9 @@ int cfm_plan_dot_cost(const float* M, int n0, int n1, int64_t ldm, float reg,
  * uniform plan is sampled instead and CFM_FLAG_ZERO_MASS is set (:93-96).
  * uniform_rows != 0: the potentials come from a solve whose last update was the row update
  * (always true for cfm_sinkhorn_log_f32), so every row has mass exactly 1/n0: the row-mass
- * pass is skipped and the within-row inversion runs in fp32 (one launch, two row passes).
+ * pass is skipped and the within-row inversion weighs column j by pi_ij itself (exponent
+ * -M_ij/reg + log_u_i + log_v_j <= 0: no under/overflow at any |M/reg|; formed in fp32 when
+ * |M/reg| <= 64 and with float64 adds beyond, the rule cfm_sinkhorn_log_f32's auto mode uses).
  */
 size_t cfm_plan_sample_workspace_bytes(int n0);
 int cfm_plan_sample(const float* M, int n0, int n1, int64_t ldm, float reg,
@@ -125,11 +129,13 @@ int cfm_plan_sample(const float* M, int n0, int n1, int64_t ldm, float reg,
 /* row-conditional draw, replaces the per-sample loop of OTPlanSampler.sample_trajectory
  * (optimal_transport.py:239-248: np.random.choice(n1, p=pi[i] / pi[i].sum()) for i in rows):
  * j_out[k] = searchsorted(cumsum(pi[rows[k], :]) / sum(pi[rows[k], :]), uniforms[k], 'right') with
- * the plan row recomputed from (M, log_v); log_u cancels in the row normalisation. */
+ * the plan row recomputed from (M, log_v).  log_u cancels in the row normalisation; it is used (when not
+ * NULL) only to centre the exponents, -M_ij/reg + log_u_i + log_v_j = log pi_ij <= 0, so that no row can
+ * under- or overflow at large |M/reg|; with log_u == NULL a row-maximum pass does the centring. */
 int cfm_plan_sample_rows(const float* M, int n0, int n1, int64_t ldm, float reg,
-                         const float* cost_max, int normalize, const double* log_v,
-                         const int64_t* rows, const double* uniforms, int n_draws,
-                         int64_t* j_out, int32_t* status, void* stream);
+                         const float* cost_max, int normalize, const double* log_u,
+                         const double* log_v, const int64_t* rows, const double* uniforms,
+                         int n_draws, int64_t* j_out, int32_t* status, void* stream);
 /* same draw for a dense float64 plan already in device memory (staged parity test) */
 int cfm_dense_plan_sample_f64(const double* plan, int n0, int n1, const double* uniforms,
                               int n_draws, int64_t* i_out, int64_t* j_out,
@@ -204,11 +210,13 @@ int cfm_mlp_forward_f32(const void* prepared, const float* x, int batch, int dim
                         int act, float* y, int algo, void* workspace,
                         size_t workspace_bytes, void* stream);
 
-/* Same forward for an input that already exists as its TF32 operand split (x = x_hi + x_lo, as
- * written by cfm_rk_stage_input); tensor-core path only.  cfm_mlp_tc_supported() != 0 tells whether
- * a shape runs on it. */
+/* Same forward for an input that already exists as the tensor-core operand pair of the fp16x3 scheme
+ * (fp16 arrays of B*dim elements: x_hi = fp16(x), x_lo = fp16((x - x_hi) * 2048), as written by
+ * cfm_rk_stage_input); tensor-core paths only: ONE fused persistent launch for 256-wide hidden layers
+ * (activations stay in shared memory), per-layer GEMM launches otherwise.  cfm_mlp_tc_supported() != 0
+ * tells whether a shape runs on them. */
 int cfm_mlp_tc_supported(int batch, int dim, int w, int out_dim);
-int cfm_mlp_forward_split_f32(const void* prepared, const float* x_hi, const float* x_lo, int batch,
+int cfm_mlp_forward_split_f32(const void* prepared, const void* x_hi, const void* x_lo, int batch,
                               int dim, int w, int out_dim, int time_varying, const float* t_dev,
                               float t_host, int act, float* y, void* workspace,
                               size_t workspace_bytes, void* stream);
@@ -238,11 +246,11 @@ typedef struct cfm_rk_state {
 
 /* stage in 1..5: out = x + dt*sum_j a[stage][j]*k_j (input of stage+1's evaluation);
  * stage 6: the same with the 5th-order weights, i.e. out = xnew (and the FSAL input).
- * out (nullable) receives the fp32 value; out_hi/out_lo (nullable pair) receive its TF32 operand
- * split, the form cfm_mlp_forward_split_f32 consumes.  *t_stage (device float, nullable) =
- * t + c[stage]*dt. */
+ * out (nullable) receives the fp32 value; out_hi/out_lo (nullable pair, fp16 arrays of numel elements)
+ * receive its fp16x3 operand split, the form cfm_mlp_forward_split_f32 consumes.  *t_stage (device
+ * float, nullable) = t + c[stage]*dt. */
 int cfm_rk_stage_input(const cfm_rk_state* st, const float* x, const float* k, float* out,
-                       float* out_hi, float* out_lo, float* t_stage, int64_t numel, int stage,
+                       void* out_hi, void* out_lo, float* t_stage, int64_t numel, int stage,
                        void* stream);
 /* st->err_acc += sum((dt*sum_j e_j k_j / (atol + rtol*max(|x|,|xnew|)))^2) */
 int cfm_rk_error_norm(cfm_rk_state* st, const float* x, const float* xnew, const float* k,
@@ -258,6 +266,17 @@ int cfm_rk_init_a(cfm_rk_state* st, const float* x, const float* f0, float* x_pr
                   float* t_stage, double* scratch, int64_t numel, void* stream);
 int cfm_rk_init_b(cfm_rk_state* st, const float* x, const float* f0, const float* f1,
                   const float* t_span, double* scratch, int64_t numel, void* stream);
+/* The same initial-step computation in its four stages, for row-sharded (lock-step) integration across
+ * ranks: cfm_rk_init_sums accumulates this shard's partial sums into scratch
+ * (phase 0: zeroes scratch, then sum (x/scale)^2 and sum (f0/scale)^2; phase 1: sum ((f1-f0)/scale)^2);
+ * the driver all-reduces scratch over the ranks; probe / finish then take the GLOBAL element count.
+ * cfm_rk_control's numel is likewise the global count when st->err_acc has been all-reduced. */
+int cfm_rk_init_sums(const cfm_rk_state* st, const float* x, const float* f0, const float* f1,
+                     double* scratch, int64_t numel, int phase, void* stream);
+int cfm_rk_init_probe(cfm_rk_state* st, const float* x, const float* f0, float* x_probe, float* t_stage,
+                      const double* scratch, int64_t numel, int64_t numel_global, void* stream);
+int cfm_rk_init_finish(cfm_rk_state* st, const float* t_span, const double* scratch, int64_t numel_global,
+                       void* stream);
 /* x_out = x + h * k  (fixed-step Euler, torchdyn solver="euler") */
 int cfm_axpy_f32(const float* x, const float* k, float h, float* x_out, int64_t numel,
                  void* stream);

@@ -53,9 +53,12 @@ def emd(a, b, M, numItermax=100000, log=False, center_dual=True, numThreads=1,
 
     POT casts a, b, M to float64 C-order and runs a network simplex; the result
     is an optimal vertex of the transport polytope.  For a = b = 1/N that vertex
-    is a permutation matrix / N.  Non-uniform or rectangular inputs are outside
-    the reference hot path (OTPlanSampler always passes pot.unif marginals of the
-    two batch sizes) and raise here.
+    is a permutation matrix / N.  Uniform marginals of DIFFERENT sizes (what
+    OTPlanSampler passes when the two batches differ, optimal_transport.py:79)
+    are solved as the transport LP itself with SciPy's HiGHS simplex -- an
+    independent exact LP solver; the optimum is unique almost surely for
+    continuous data, so it is the vertex POT's network simplex returns.
+    Non-uniform marginals are outside the reference hot path and raise.
     """
     a, b, M = _as_f64_c(a), _as_f64_c(b), _as_f64_c(M)
     if a.size == 0:
@@ -63,15 +66,37 @@ def emd(a, b, M, numItermax=100000, log=False, center_dual=True, numThreads=1,
     if b.size == 0:
         b = np.ones((M.shape[1],)) / M.shape[1]
     n0, n1 = M.shape
-    if n0 != n1 or not (np.allclose(a, 1.0 / n0) and np.allclose(b, 1.0 / n1)):
+    if not (np.allclose(a, 1.0 / n0) and np.allclose(b, 1.0 / n1)):
         raise NotImplementedError(
-            "oracle ot.emd restates POT only for uniform equal-size marginals "
-            "(the only case OTPlanSampler produces with equal batch sizes)")
+            "oracle ot.emd restates POT only for uniform marginals "
+            "(the only case OTPlanSampler produces)")
+    if n0 != n1:
+        G = _transport_lp(a, b, M)
+        if log:
+            return G, {"cost": float((G * M).sum()), "warning": None}
+        return G
     row, col = linear_sum_assignment(M)
     G = np.zeros((n0, n1), dtype=np.float64)
     G[row, col] = a[row]
     if log:
         return G, {"cost": float((G * M).sum()), "warning": None}
+    return G
+
+
+def _transport_lp(a, b, M):
+    """min <G, M>  s.t.  G 1 = a, G^T 1 = b, G >= 0  (dual simplex, vertex solution)."""
+    from scipy.optimize import linprog
+    from scipy.sparse import kron, eye, csr_matrix
+    n0, n1 = M.shape
+    A_rows = kron(eye(n0), np.ones((1, n1)))          # row sums
+    A_cols = kron(np.ones((1, n0)), eye(n1))          # column sums
+    A = csr_matrix(np.vstack([A_rows.toarray(), A_cols.toarray()[:-1]]))  # drop one redundant constraint
+    rhs = np.concatenate([a, b[:-1]])
+    res = linprog(M.reshape(-1), A_eq=A, b_eq=rhs, bounds=(0, None), method="highs-ds")
+    if res.status != 0:
+        raise RuntimeError(f"oracle transport LP failed: {res.message}")
+    G = res.x.reshape(n0, n1)
+    G[np.abs(G) < 1e-15] = 0.0
     return G
 
 
