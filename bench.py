@@ -8,10 +8,11 @@ minibatch-OT couplings/sec (N=8192, d=784) [+ ODE samples/sec], 1..8 B200 of one
     python bench.py --impl reference ...      # the reference's CPU path (oracle port) on host cores
 
 One step = one full coupling `OTPlanSampler("sinkhorn", reg=0.05, normalize_cost=True).sample_plan`
-(cost matrix + 100 log-domain Sinkhorn iterations, stopThr=0 + N pair draws + gather) on a fresh
-pair of synthetic Gaussian batches; weak scaling: every rank couples its own N=8192 shard
-(per-shard coupling, the only collective is the NCCL all-gather of the sampled index pairs).
-Rank 0 prints ONE JSON line.
+(cost matrix + 100 log-domain Sinkhorn iterations, stopThr=0 + N pair draws + gather) on a
+pair of synthetic Gaussian batches resident in HBM; weak scaling: every rank couples its own N=8192 shard
+(per-shard coupling, the only collective is the NCCL all-gather of the sampled index pairs, issued on a side
+stream).  Rank 0 prints ONE JSON line; besides the contract's keys it carries sub-records for the other BASELINE
+configs (c1_coupling, c4, c5, ode, ode_c1, ode_strong), each with its parity gate.
 """
 import argparse
 import json
@@ -32,6 +33,7 @@ METRIC = "minibatch-OT couplings/sec (N=8192,d=784)"
 WORKLOAD = ("C2: Sinkhorn minibatch coupling N=8192 d=784 fp32, 100 log-domain iterations "
             "(normalize_cost=True, reg=0.05, stopThr=0): cost matrix + solve + 8192 pair draws + gather")
 ODE_B, ODE_DIM, ODE_W = 10000, 784, 256
+REF_BUDGET_S = 150.0  # wall budget of the timed steps of `--impl reference` (each step is one FULL coupling)
 
 
 def peaks():
@@ -52,7 +54,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "50", "-i", str(index)], stdout=self.f,
+                                       "-lms", "100", "-i", str(index)], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -86,116 +88,113 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ CPU reference arm
-def cpu_reference_sample(n_iter_sample=3, seed=0):
-    """The reference's CPU path for ONE C2 coupling, restated (oracle/coupling.py + oracle/ot):
-    torch.cdist**2 -> POT's kernel-space sinkhorn_knopp (what OTPlanSampler('sinkhorn') calls;
-    finite in this normalised regime) -> np.random.choice -> gather.  Bounded sample: the cost
-    matrix, exp(-M/reg), plan formation and the pair draw are timed in full; the Sinkhorn loop is
-    timed for `n_iter_sample` iterations and scaled to 100."""
-    from oracle import coupling as oc
-    from oracle import ot as oot  # noqa: F401
-    g = torch.Generator().manual_seed(seed)
-    x0, x1 = torch.randn(N, D, generator=g), torch.randn(N, D, generator=g)
-    t = {}
-    t0 = time.perf_counter()
-    M = oc.cost_matrix(x0, x1, normalize_cost=True)
-    Mn = M.detach().cpu().numpy()
-    t["cost"] = time.perf_counter() - t0
-    a = b = np.ones(N) / N
-    t0 = time.perf_counter()
-    K = np.exp(Mn / (-REG))
-    Kp = (1 / a).reshape(-1, 1) * K
-    u = np.ones(N, dtype=Mn.dtype) / N
-    t["setup"] = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    for _ in range(n_iter_sample):
-        v = b / np.dot(K.T, u)
-        u = 1.0 / np.dot(Kp, v)
-    t["iter"] = (time.perf_counter() - t0) / n_iter_sample
-    t0 = time.perf_counter()
-    P = u.reshape((-1, 1)) * K * v.reshape((1, -1))
-    i, j = oc.draw_pairs(P, N)
-    _ = x0[i], x1[j]
-    t["draw"] = time.perf_counter() - t0
-    total = t["cost"] + t["setup"] + ITERS * t["iter"] + t["draw"]
-    return 1.0 / total, t
+class CpuReference:
+    """The reference's CPU path for one C2 coupling, restated (oracle/coupling.py + oracle/ot; POT itself is not
+    installable here): torch.cdist**2 / max -> POT's KERNEL-SPACE sinkhorn_knopp with POT's dtype pattern (fp32 K,
+    float64 Kp and vectors; this is what OTPlanSampler('sinkhorn') calls and it is finite in this normalised
+    regime) for exactly 100 iterations -> u K v plan -> np.random.choice over the flattened plan -> gather.
+    Every part is executed in full; nothing is extrapolated."""
 
+    def __init__(self, seed=0):
+        g = torch.Generator().manual_seed(seed)
+        self.x0, self.x1 = torch.randn(N, D, generator=g), torch.randn(N, D, generator=g)
 
-class _CpuState:
-    """Inputs and the kernel matrix of the CPU reference sample, built once per process."""
-    x0 = x1 = K = Kp = u = None
-    fixed = None  # timings of the parts measured once: cost, setup, draw
-
-
-def cpu_reference_iterations(n_iter):
-    """Re-time only the Sinkhorn-Knopp loop of the reference CPU path (bounded step of --impl reference)."""
-    S = _CpuState
-    if S.K is None:
+    def coupling(self):
         from oracle import coupling as oc
-        g = torch.Generator().manual_seed(0)
-        S.x0, S.x1 = torch.randn(N, D, generator=g), torch.randn(N, D, generator=g)
+        t = {}
         t0 = time.perf_counter()
-        Mn = oc.cost_matrix(S.x0, S.x1, normalize_cost=True).detach().cpu().numpy()
-        t_cost = time.perf_counter() - t0
+        Mn = oc.cost_matrix(self.x0, self.x1, normalize_cost=True).detach().cpu().numpy()
+        t["cost"] = time.perf_counter() - t0
+        a = b = np.ones(N) / N
         t0 = time.perf_counter()
-        S.K = np.exp(Mn / (-REG))
-        S.Kp = (N * 1.0) * S.K
-        S.u = np.ones(N, dtype=Mn.dtype) / N
-        t_setup = time.perf_counter() - t0
-        b = np.ones(N) / N
-        v = b / np.dot(S.K.T, S.u)
-        u = 1.0 / np.dot(S.Kp, v)
+        K = np.exp(Mn / (-REG))                 # fp32
+        Kp = (1 / a).reshape(-1, 1) * K         # float64 (POT dtype pattern)
+        u = np.ones(N, dtype=Mn.dtype) / N
+        t["setup"] = time.perf_counter() - t0
         t0 = time.perf_counter()
-        P = u.reshape((-1, 1)) * S.K * v.reshape((1, -1))
+        for _ in range(ITERS):
+            v = b / np.dot(K.T, u)
+            u = 1.0 / np.dot(Kp, v)
+        t["iters"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        P = u.reshape((-1, 1)) * K * v.reshape((1, -1))
         i, j = oc.draw_pairs(P, N)
-        _ = S.x0[i], S.x1[j]
-        del P
-        S.fixed = {"cost": t_cost, "setup": t_setup, "draw": time.perf_counter() - t0}
-    b = np.ones(N) / N
-    u = S.u
-    t0 = time.perf_counter()
-    for _ in range(n_iter):
-        v = b / np.dot(S.K.T, u)
-        u = 1.0 / np.dot(S.Kp, v)
-    t_iter = (time.perf_counter() - t0) / n_iter
-    parts = dict(S.fixed, iter=t_iter)
-    return 1.0 / (parts["cost"] + parts["setup"] + ITERS * t_iter + parts["draw"]), parts
+        _ = self.x0[i], self.x1[j]
+        t["draw"] = time.perf_counter() - t0
+        return sum(t.values()), t
 
 
 def run_reference_arm(args, rank):
-    """`bench.py --impl reference`: the reference's own CPU implementation of the path (POT is not
-    installable here, so its restatement in oracle/: kind "port") on all host cores.  The cost matrix,
-    exp(-M/reg), plan formation, np.random.choice and the gather are timed in full ONCE per process;
-    every step re-times 2 Sinkhorn-Knopp iterations (the part that is 100x per coupling) and the value
-    of a step is 1 / (cost + setup + 100 * iter + draw)."""
+    """`bench.py --impl reference`: every step is ONE COMPLETE coupling of the reference's CPU path (kind "port":
+    the oracle restatement, kernel-space Sinkhorn-Knopp like the reference) on all host cores.  A coupling takes tens
+    of seconds here, so the number of timed steps is bounded by a wall budget (at least one, at most --steps) and
+    reported as `steps`; `steps_requested` keeps the driver's K."""
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    for _ in range(max(1, args.warmup)):
-        cpu_reference_iterations(1)
-    vals, parts = [], None
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        v, parts = cpu_reference_iterations(2)
-        vals.append(v)
-    wall = time.perf_counter() - t0
-    value = float(np.mean(vals))
+    ref = CpuReference(0)
+    np.dot(np.ones((512, 512), np.float32), np.ones(512, np.float32))  # BLAS thread pool spin-up (the only warm-up)
+    times, parts = [], None
+    t_begin = time.perf_counter()
+    while len(times) < max(1, args.steps):
+        dt, parts = ref.coupling()
+        times.append(dt)
+        if time.perf_counter() - t_begin + dt > REF_BUDGET_S:
+            break
+    wall = time.perf_counter() - t_begin
+    value = len(times) / sum(times)
     cores = os.cpu_count() or 1
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "couplings/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "n_gpus": args.gpus, "steps": len(times), "steps_requested": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU path, one coupling stream regardless of --gpus; "
-                   f"wall time of the {args.steps} bounded steps: {wall:.1f} s"},
+        "config": {"workload": WORKLOAD, "solver": "kernel-space Sinkhorn-Knopp (POT sinkhorn_knopp restated), 100 iterations",
+                   "note": "CPU path, one coupling stream regardless of --gpus; every step is a complete coupling; the "
+                           "warm-up is the BLAS thread-pool spin-up only (a warm-up coupling would cost a whole step); "
+                           f"timed wall {wall:.1f} s for {len(times)} step(s), budget {REF_BUDGET_S:.0f} s"},
         "cpu_baseline": {"value": value, "unit": "couplings/s", "cores": cores, "kind": "port",
-                         "sample": "cdist**2, exp(-M/reg), plan, np.random.choice, gather timed in full once; per step "
-                                   "2 Sinkhorn-Knopp iterations timed and scaled to 100; "
-                                   f"parts(s)={ {k: round(v, 4) for k, v in parts.items()} }"},
+                         "sample": f"{len(times)} complete N=8192,d=784 coupling(s): cdist**2/max, exp(-M/reg), 100 Knopp "
+                                   "iterations (fp32 K, float64 Kp/u/v), plan, np.random.choice, gather; "
+                                   f"parts(s) of the last one={ {k: round(v, 3) for k, v in parts.items()} }"},
         "e2e": {"value": value, "unit": "couplings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "step_ms": {"median": float(np.median(times) * 1e3), "min": float(min(times) * 1e3), "max": float(max(times) * 1e3)},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------ helpers (GPU arm)
+def eight_gaussians(n, gen):
+    """utils.sample_8gaussians restated (torchcfm/utils.py:11-41): radius-5 octagon, per-axis std 0.1**0.25."""
+    ang = torch.arange(8) * (2 * np.pi / 8)
+    centers = 5.0 * torch.stack([torch.cos(ang), torch.sin(ang)], 1)
+    k = torch.randint(0, 8, (n,), generator=gen)
+    return (centers[k] + (0.1 ** 0.25) * torch.randn(n, 2, generator=gen)).float()
+
+
+def two_moons(n, gen):
+    """utils.sample_moons restated (torchcfm/utils.py:35-37): generate_moons(n, noise=0.2) * 3 - 1."""
+    n_out = n // 2
+    to, ti = torch.linspace(0, np.pi, n_out), torch.linspace(0, np.pi, n - n_out)
+    x = torch.cat([torch.stack([torch.cos(to), torch.sin(to)], 1),
+                   torch.stack([1 - torch.cos(ti), 1 - torch.sin(ti) - 0.5], 1)], 0)
+    x = x + 0.2 * torch.randn(n, 2, generator=gen)
+    return (x[torch.randperm(n, generator=gen)] * 3 - 1).float()
+
+
+def timed_ms(fn, reps, dev, warm=2):
+    """Mean device time of fn() over `reps` back-to-back calls (CUDA events on the current stream)."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1) / reps
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -207,6 +206,7 @@ def main():
     ap.add_argument("--impl", default="cfm_b200", choices=["cfm_b200", "reference"])
     ap.add_argument("--no-ode", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the c1/c4/c5 sub-records")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cfm_b200" else args.warmup
 
@@ -221,6 +221,8 @@ def main():
     import cfm_b200
     from cfm_b200 import _ffi
     from cfm_b200 import dist as cdist
+    from oracle import coupling as oc
+    from oracle import vector_field as vf
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -235,6 +237,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # synthetic inputs: generated on the CPU (identical bits for the CPU baseline), distinct per rank
     g = torch.Generator().manual_seed(rank)
     x0_h = torch.randn(N, D, generator=g).pin_memory()
@@ -244,9 +252,15 @@ def main():
                                      stop_thr=0.0, warn=False)
     np.random.seed(1234 + rank)
 
+    pending = []
+
     def step():
         if world > 1:
-            return cdist.sharded_sample_plan(sampler, x0, x1)
+            a, b, h = cdist.sharded_sample_plan(sampler, x0, x1, async_gather=True)
+            pending.append(h)  # the index all-gather overlaps the next coupling; picked up below
+            if len(pending) > 1:
+                pending.pop(0).wait()
+            return a, b
         return sampler.sample_plan(x0, x1)
 
     # nvidia-smi is started BEFORE the warm-up (its start-up stalls the GPU for a few ms) and keeps
@@ -261,25 +275,26 @@ def main():
     # ---- timed region: K steps, device events, barrier + synchronize both sides ----
     sampler.stage_events = []
     launches0 = L.cfm_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
-    ev0.record()
-    for _ in range(args.steps):
+    marks[0].record()
+    for k in range(args.steps):
         out = step()
-    ev1.record()
+        marks[k + 1].record()
+    while pending:
+        pending.pop(0).wait()
     barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
+    elapsed_ms = marks[0].elapsed_time(marks[-1])
+    per_step = [marks[k].elapsed_time(marks[k + 1]) for k in range(args.steps)]
     launches = L.cfm_launch_count() - launches0
     clk = clocks.stop() if clocks else None
     stage_ms = {}
     for name, a, b in sampler.stage_events:
         stage_ms.setdefault(name, []).append(a.elapsed_time(b))
     sampler.stage_events = None
-    tmax = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(tmax.item())
+    elapsed_ms = max_over_ranks(elapsed_ms)
     value = world * args.steps / (elapsed_ms * 1e-3)
+    assert out[0].shape == (N, D) and out[0].is_cuda
 
     # ---- parity gate reported with the number: marginals of the implied plan (float64, device)
     cp = sampler._couple(x0, x1, dev)
@@ -305,9 +320,6 @@ def main():
     # batch k's solve on separate streams.  This is the headline e2e number.
     from cfm_b200 import CouplingStream
     pipe = CouplingStream(sampler, dev, depth=2)
-    # one continuous stream of warm + K batches; the clock starts when result number `warm` is delivered, so
-    # the timed window holds exactly K steady-state steps (each with its own upload and download) and not the
-    # pipeline fill or the one-off growth of torch's pinned / device allocator pools
     warm = 6
     n_out = -warm
     t0 = None
@@ -319,31 +331,44 @@ def main():
     e2e_s = time.perf_counter() - t0
     torch.cuda.synchronize(dev)
     assert n_out == args.steps
-    te = torch.tensor([e2e_s, single_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e = {"value": world * args.steps / float(te[0].item()), "unit": "couplings/s",
+    e2e_s, single_s = max_over_ranks(e2e_s), max_over_ranks(single_s)
+    e2e = {"value": world * args.steps / e2e_s, "unit": "couplings/s",
            "h2d_bytes_per_step": int(2 * N * D * 4 + N * 8), "d2h_bytes_per_step": int(2 * N * D * 4),
            "api": "CouplingStream(sampler).map(host batches), depth 2; K consecutive steady-state results timed "
                   "after 6 untimed ones of the same stream",
-           "blocking_call_value": world * args.steps / float(te[1].item())}
+           "blocking_call_value": world * args.steps / single_s}
     assert a_h.device.type == "cpu" and a_h.shape == (N, D)
 
-    # ---- roofline of the dominant kernel (the persistent Sinkhorn sweep kernel) ----
+    # ---- roofline of the dominant kernel (the persistent Sinkhorn sweep kernel) + the tensor-core kernels ----
     hbm_peak, tc_peak, which = peaks()
     solve_ms = float(np.mean(stage_ms["solve"]))
-    alg_bytes = ITERS * 2 * N * N * 4  # two passes over M per iteration
-    achieved = alg_bytes / (solve_ms * 1e-3) / 1e9
+    cost_ms = float(np.mean(stage_ms["cost"]))
+    one_pass = ITERS * N * N * 4  # the fused sweep reads M once per iteration (row AND column update per pass)
+    achieved = one_pass / (solve_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("sinkhorn_kernel_dram_bytes_per_launch")
+    kernels = [{"kernel": "gemm_h3_kernel<256, SqDistH3Epilogue> + 2 prep_rows_h3 (stage 'cost')", "bound": "tensor",
+                "ms": cost_ms, "algorithmic_tflops": 2.0 * N * N * D / (cost_ms * 1e-3) / 1e12,
+                "issued_tflops_f16": 3 * 2.0 * N * N * D / (cost_ms * 1e-3) / 1e12, "peak_tflops_f16": tc_peak,
+                "frac_issued": 3 * 2.0 * N * N * D / (cost_ms * 1e-3) / 1e12 / tc_peak,
+                "note": "fp16x3 scheme: three kind::f16 MMAs per product for fp32-grade accuracy; the stage time "
+                        "includes the two row pre-passes (norms, scales, operand split)"}]
     roofline = {"bound": "hbm", "kernel": "sinkhorn_v2_kernel<512,4,2> (100 fused sweeps, one cooperative launch)",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "frac_one_pass": achieved / hbm_peak,
+                "frac_dram": (traffic / (solve_ms * 1e-3) / 1e9 / hbm_peak) if traffic else None,
                 "traffic": traffic, "peak_source": which,
-                "note": "algorithmic bytes = iters*2*N^2*4 (two passes per iteration); the fused sweep "
-                        "reads M from HBM once per iteration, so frac can exceed 1",
-                "stage_ms": {k: float(np.mean(v)) for k, v in stage_ms.items()}}
+                "algorithmic_bytes": one_pass,
+                "survey_8d": {"bytes": 2 * one_pass, "gbs": 2 * achieved,
+                              "note": "SURVEY 8(d) counts two passes over M per iteration; the fused sweep makes one, "
+                                      "so this figure is a labelled aside, not a fraction of peak"},
+                "note": "frac = one-pass algorithmic bytes (iters*N^2*4) / solve time / measured HBM peak; frac_dram "
+                        "= ncu DRAM bytes of the same kernel (profiles/roofline_traffic.json) / solve time / peak: "
+                        "part of M stays L2-resident between sweeps, so DRAM traffic is below the one-pass bytes",
+                "stage_ms": {k: float(np.mean(v)) for k, v in stage_ms.items()},
+                "kernels": kernels}
 
     line = {
         "metric": METRIC, "value": value, "unit": "couplings/s", "n_gpus": world, "steps": args.steps,
@@ -353,7 +378,75 @@ def main():
                    "l2": "inputs larger than L2: the cost matrix streamed every iteration is 268 MB"},
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         "parity": parity,
+        "step_ms": {"median": float(np.median(per_step)), "min": float(min(per_step)), "max": float(max(per_step)),
+                    "note": "per-step device time of rank 0 (events between steps)"},
     }
+
+    # ---- the other BASELINE configs, each with its parity gate (rank-local work; max over ranks reported) ----
+    if not args.no_extra:
+        # C1: 8gaussians -> 2moons, exact OT, batch 256 (examples/2D_tutorials)
+        gen = torch.Generator().manual_seed(10 + rank)
+        a8, m2 = eight_gaussians(256, gen), two_moons(256, gen)
+        a8d, m2d = a8.to(dev), m2.to(dev)
+        ex = cfm_b200.OTPlanSampler("exact")
+        pi = ex.get_map(a8d, m2d)
+        sig_ok = bool(np.array_equal(pi.argmax(1), oc.assignment(oc.cost_matrix(a8, m2))))
+        np.random.seed(77)
+        c1_ms = timed_ms(lambda: ex.sample_plan(a8d, m2d), 50, dev, warm=5)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            np.random.seed(77)
+            oc.sample_plan(a8, m2, "exact")
+        c1_cpu_ms = (time.perf_counter() - t0) / 20 * 1e3
+        line["c1_coupling"] = {"config": "C1: 8gaussians->2moons exact OT coupling, batch 256, d=2 (cost + exact assignment "
+                                         "+ 256 pair draws + gather, status word read every call)",
+                               "ms_per_coupling": max_over_ranks(c1_ms), "couplings_per_s": world * 1e3 / max_over_ranks(c1_ms),
+                               "sigma_bit_exact_vs_scipy": sig_ok, "dijkstra_steps": ex.last_info.get("dijkstra_steps"),
+                               "cpu_reference_port_ms": c1_cpu_ms if rank == 0 else None}
+
+        # C4: SB-CFM entropic OT eps = 2 sigma^2 = 0.1, N = 16384 d = 512 in 4 shards of 4096 (per-shard coupling)
+        fm = cfm_b200.SchrodingerBridgeConditionalFlowMatcher(sigma=0.05 ** 0.5, ot_method="sinkhorn")
+        sb = fm.ot_sampler
+        sb.num_iter_max, sb.stop_thr, sb.warn = 100, 0.0, False
+        g4 = torch.Generator().manual_seed(40 + rank)
+        y0, y1 = torch.randn(4096, 512, generator=g4).to(dev), torch.randn(4096, 512, generator=g4).to(dev)
+        np.random.seed(4)
+        c4_ms = timed_ms(lambda: sb.sample_plan(y0, y1), 5, dev, warm=2)
+        cp4 = sb._couple(y0, y1, dev)
+        i4, j4 = sb._draw(cp4, 4096)
+        Mr = -(cp4.M[:, :4096] / np.float32(sb.reg)).double()
+        P4 = (Mr + cp4.log_u[:, None] + cp4.log_v[None, :]).exp()
+        st4 = cp4.status.cpu().tolist()
+        line["c4"] = {"config": "C4: SB-CFM entropic coupling eps=0.1 (un-normalised cost, |M/eps| ~ 1e4: float64-potential "
+                                "mode), shards of 4096 x 4096, d=512, 100 iterations, one shard per GPU "
+                                f"({world} shard(s) in this run; BASELINE: 4)",
+                      "ms_per_shard_coupling": max_over_ranks(c4_ms), "shard_couplings_per_s": world * 1e3 / max_over_ranks(c4_ms),
+                      "arithmetic": {0: "fp32", 1: "fp64", 2: "fp64-mixed"}.get(st4[2], st4[2]),
+                      "row_marginal_max_rel_err": float((P4.sum(1) * 4096 - 1).abs().max().item()),
+                      "draw_flags": st4[0] & 3,
+                      "note": "row marginals are exact by construction after the final row update; the column marginals of "
+                              "this un-converged regime are far from uniform after 100 iterations for ANY log-domain solver "
+                              "(SURVEY finding 11-ii); the reference's own kernel-space path underflows here and silently "
+                              "returns the uniform plan"}
+        del P4, Mr, cp4
+
+        # C5: Sinkhorn sweep N in {1k, 4k, 16k, 64k} d = 128 over 8 shards -> per-shard sizes 128 ... 8192
+        c5 = []
+        s5 = cfm_b200.OTPlanSampler("sinkhorn", reg=REG, normalize_cost=True, num_iter_max=ITERS, stop_thr=0.0, warn=False)
+        for ns in (128, 512, 2048, 8192):
+            g5 = torch.Generator().manual_seed(50 + rank + ns)
+            z0, z1 = torch.randn(ns, 128, generator=g5).to(dev), torch.randn(ns, 128, generator=g5).to(dev)
+            np.random.seed(5)
+            ms = timed_ms(lambda: s5.sample_plan(z0, z1), 10 if ns < 8192 else 5, dev, warm=2)
+            cp5 = s5._couple(z0, z1, dev)
+            P5 = (-((cp5.M[:, :ns] / cp5.cost_max).double() / REG) + cp5.log_u[:, None] + cp5.log_v[None, :]).exp()
+            c5.append({"n_global_at_8_shards": 8 * ns, "n_per_shard": ns, "ms_per_shard_coupling": max_over_ranks(ms),
+                       "pairs_per_s": world * ns * 1e3 / max_over_ranks(ms),
+                       "col_marginal_max_rel_err": float((P5.sum(0) * ns - 1).abs().max().item())})
+            del P5, cp5
+        line["c5"] = {"config": f"C5: Sinkhorn sweep d=128, reg=0.05 normalised, 100 iterations, per-shard sizes of the "
+                                f"8-way sharded N in {{1k,4k,16k,64k}}; {world} shard(s) in this run (BASELINE: 8)",
+                      "sweep": c5}
 
     # ---- second half of the metric: ODE samples/sec (BASELINE config 3) ----
     if not args.no_ode:
@@ -372,21 +465,30 @@ def main():
             node.trajectory(xo, span)
         e1.record()
         barrier()
-        tm = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        ode_s = float(tm.item()) * 1e-3 / reps
+        ode_s = max_over_ranks(e0.elapsed_time(e1)) * 1e-3 / reps
         nfe = node.stats["nfe"]
         flops = 2.0 * ODE_B * (785 * 256 + 256 * 256 + 256 * 256 + 256 * 784) * nfe
+        # the forward alone (one fused launch + the fp32 -> fp16x3 split of its input)
+        yb = torch.empty_like(xo)
+        fwd_ms = timed_ms(lambda: mlp.vector_field(0.5, xo, out=yb), 50, dev, warm=5)
+        fwd_flops = 2.0 * ODE_B * (785 * 256 + 256 * 256 + 256 * 256 + 256 * 784)
         line["ode"] = {"metric": "ODE samples/sec (MLP 785-256-256-256-784 SELU, dopri5 atol=rtol=1e-4, B=10000/GPU)",
                        "value": world * ODE_B / ode_s, "unit": "samples/s", "nfe": nfe,
                        "accepted": node.stats["accepted"], "rejected": node.stats["rejected"],
                        "ms_per_trajectory": ode_s * 1e3, "mlp_tflops_algorithmic": flops / ode_s / 1e12,
-                       "mlp_rows_per_s_per_nfe": world * ODE_B * nfe / ode_s}
+                       "mlp_rows_per_s_per_nfe": world * ODE_B * nfe / ode_s,
+                       "mlp_launches_per_nfe": 1 if mlp.w == 256 else 4,
+                       "mlp_forward_ms": fwd_ms}
+        roofline["kernels"].append({"kernel": "mlp_fused_h3_kernel (whole 4-layer forward, one launch) + input split",
+                                    "bound": "tensor", "ms": fwd_ms,
+                                    "algorithmic_tflops": fwd_flops / (fwd_ms * 1e-3) / 1e12,
+                                    "issued_tflops_f16": 3 * fwd_flops / (fwd_ms * 1e-3) / 1e12, "peak_tflops_f16": tc_peak,
+                                    "frac_issued": 3 * fwd_flops / (fwd_ms * 1e-3) / 1e12 / tc_peak,
+                                    "note": "79 row slabs of 128 on 148 SMs (B = 10000): at most 53% of the tensor pipes "
+                                            "can be busy in this one-slab-per-CTA design"})
         if rank == 0:
             # comparator on the same GPU: stock PyTorch eager (cuBLAS sgemm, TF32 off) through the
             # oracle's torchdyn-style driver
-            from oracle import vector_field as vf
             torch.backends.cuda.matmul.allow_tf32 = False
             ref_m = vf.make_mlp(ODE_DIM, w=ODE_W, time_varying=True).to(dev)
             ref_m.load_state_dict(mlp.state_dict())
@@ -399,6 +501,28 @@ def main():
                 vf.dopri5_trajectory(f, xo, span.to(dev))
             torch.cuda.synchronize(dev)
             line["ode"]["torch_eager_same_gpu_samples_per_s"] = ODE_B / ((time.perf_counter() - t0) / 3)
+        barrier()
+
+        # ---- strong scaling of C3 with row sharding: B = 10000 split over the ranks ----
+        if world > 1:
+            xg = torch.randn(ODE_B, ODE_DIM, generator=torch.Generator().manual_seed(100)).to(dev)  # same on all ranks
+            res = {}
+            for mode, lock in (("lockstep", True), ("independent", False)):
+                for _ in range(2):
+                    cdist.sharded_trajectory(node, xg, span, gather=False, lockstep=lock)
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(5):
+                    cdist.sharded_trajectory(node, xg, span, gather=False, lockstep=lock)
+                e1.record()
+                barrier()
+                s_ = max_over_ranks(e0.elapsed_time(e1)) * 1e-3 / 5
+                res[mode] = {"samples_per_s": ODE_B / s_, "ms_per_trajectory": s_ * 1e3, "nfe": node.stats["nfe"],
+                             "accepted": node.stats["accepted"], "rejected": node.stats["rejected"]}
+            line["ode_strong"] = dict(res, config=f"C3 strong scaling: B = {ODE_B} rows split over {world} ranks "
+                                                  "(weights replicated); lockstep = one float64 all-reduce per step attempt, "
+                                                  "step sequence of the single-process run; independent = per-shard controllers")
 
         # ---- BASELINE config 1 sampling: the 2-D tutorial model, launch-bound regime ----
         torch.manual_seed(0)
@@ -429,17 +553,16 @@ def main():
                 torch.cuda.synchronize(dev)
             line["ode_c1"]["torch_eager_same_gpu_samples_per_s"] = 1024 / (time.perf_counter() - t0)
 
-    # ---- CPU baseline on this box's host cores (rank 0, N=1 only) ----
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only): ONE complete coupling, nothing extrapolated ----
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
-        cpu_reference_sample(1)
-        v, parts = cpu_reference_sample(5)
+        np.dot(np.ones((512, 512), np.float32), np.ones(512, np.float32))
+        dt, parts = CpuReference(0).coupling()
         line["cpu_baseline"] = {
-            "value": v, "unit": "couplings/s", "cores": os.cpu_count() or 1, "kind": "port",
-            "sample": "one N=8192,d=784 coupling of the reference CPU path restated (torch.cdist**2, POT "
-                      "sinkhorn_knopp in NumPy, np.random.choice, gather): everything timed in full except the "
-                      "Sinkhorn loop = 5 iterations timed and scaled to 100; "
-                      f"parts(s)={ {k: round(x, 4) for k, x in parts.items()} }"}
+            "value": 1.0 / dt, "unit": "couplings/s", "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": "one COMPLETE N=8192,d=784 coupling of the reference CPU path restated (torch.cdist**2/max, POT "
+                      "kernel-space sinkhorn_knopp in NumPy with POT's dtype pattern, 100 iterations, np.random.choice, "
+                      f"gather), nothing extrapolated; parts(s)={ {k: round(x, 3) for k, x in parts.items()} }"}
     elif rank == 0:
         line["cpu_baseline"] = None
 
