@@ -213,7 +213,8 @@ __global__ void __launch_bounds__(kAsgMaxThreads, 1) assign_kernel(const AsgPara
     t = warp_sum(t);
     if (lane == 0) {
       *p.total_cost = t;
-      p.status[0] = s_bad ? CFM_FLAG_INFEASIBLE : 0;
+      // NaN costs do not stop the search (every comparison with them is false) but poison the objective
+      p.status[0] = (s_bad ? CFM_FLAG_INFEASIBLE : 0) | ((t == t && fabs(t) < 1.0e300) ? 0 : CFM_FLAG_NONFINITE);
       p.status[1] = s_naug;
       p.status[2] = s_steps;
     }
@@ -462,7 +463,7 @@ __global__ void __launch_bounds__(1024, 1) assign_fast_kernel(const AsgParams p)
     t = warp_sum(t);
     if (lane == 0) {
       *p.total_cost = t;
-      p.status[0] = bad ? CFM_FLAG_INFEASIBLE : 0;
+      p.status[0] = (bad ? CFM_FLAG_INFEASIBLE : 0) | ((t == t && fabs(t) < 1.0e300) ? 0 : CFM_FLAG_NONFINITE);
       p.status[1] = naug;
       p.status[2] = steps_total;
     }

@@ -63,11 +63,15 @@ __device__ __forceinline__ void split_h3(float v, __half& hi, __half& lo) {
   lo = __float2half_rn((v - __half2float(hi)) * kH3Scale);
 }
 // saturating variant for unscaled producers (activations): |v| > 65504 clamps instead of becoming inf
+// (cvt.rn.satfinite: one instruction per conversion)
+__device__ __forceinline__ __half f2h_satfinite(float v) {
+  unsigned short r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+  return __ushort_as_half(r);
+}
 __device__ __forceinline__ void split_h3_sat(float v, __half& hi, __half& lo) {
-  const float c = fminf(fmaxf(v, -65504.f), 65504.f);
-  hi = __float2half_rn(c);
-  const float r = (v - __half2float(hi)) * kH3Scale;
-  lo = __float2half_rn(fminf(fmaxf(r, -65504.f), 65504.f));
+  hi = f2h_satfinite(v);
+  lo = f2h_satfinite((v - __half2float(hi)) * kH3Scale);
 }
 
 // Epilogue functor interface (called by whole warps, thread = row):

@@ -183,7 +183,9 @@ struct FusedParams {
   const float* t_dev;   // device scalar or null
   float t_host;
   float* y;             // (batch, out_dim) fp32
+  unsigned long long* dbg;  // optional per-CTA globaltimer checkpoints (64 per CTA), see scripts/mlp_timeline.py
 };
+#define F_MARK(slot) do { if (p.dbg) p.dbg[blockIdx.x * 64 + (slot)] = tc_now(); } while (0)
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -209,6 +211,7 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) F_MARK(0);
   const int num_slabs = (p.batch + kTM - 1) / kTM;
   const int nk1 = (p.dim + kHK - 1) / kHK;
   const int t4 = (p.out_dim + 127) / 128;   // layer-4 tiles
@@ -235,6 +238,7 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (threadIdx.x == 0) F_MARK(1);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -288,6 +292,7 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
         const int s = q1 & 1;
         mbar_wait(&l1_full[s], (q1 >> 1) & 1);
         tc_fence_after();
+        if (lane == 0 && kc == 0 && slab == (int)blockIdx.x) F_MARK(2);
         if (lane == 0) {
           const uint32_t sa = smem_u32(s == 0 ? act : ring);
           const uint64_t ah = umma_desc_sw128(sa), al = umma_desc_sw128(sa + kHABytes);
@@ -311,6 +316,7 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
         }
         __syncwarp();
       }
+      if (lane == 0 && slab == (int)blockIdx.x) F_MARK(3);
       g += 2;
       // ---- layers 2-4: A = resident activations, B = streamed weight tiles ----
       for (int layer = 2; layer <= 4; ++layer, ++ar) {
@@ -347,6 +353,7 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
             __syncwarp();
           }
         }
+        if (lane == 0 && slab == (int)blockIdx.x) F_MARK(2 + layer);  // slots 4, 5, 6: layer's last MMA issued
       }
       if (lane == 0) tc_commit(slab_done);
       __syncwarp();
@@ -372,6 +379,7 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
           mbar_wait(&tfull[(g + 1) & 1], ((g + 1) >> 1) & 1);
         }
         tc_fence_after();
+        if (warp == 2 && lane == 0 && slab == (int)blockIdx.x && tl < 16) F_MARK(8 + 2 * tl);  // accumulators ready
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + b * 256u + (uint32_t)(half * 64);
         const float* bias = p.bias[layer - 1];
         const float* inv_ws = p.inv_ws[layer - 1];
@@ -434,12 +442,14 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core's async proxy
           mbar_arrive(&act_ready[n]);
         }
+        if (warp == 2 && lane == 0 && slab == (int)blockIdx.x && tl < 16) F_MARK(9 + 2 * tl);  // tile drained
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) F_MARK(40);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -507,6 +517,7 @@ int mlp_tc_forward(const MlpBlobHeader& h, const void* blob, const float* x, con
     p.batch = batch; p.dim = h.dim; p.out_dim = h.out_dim; p.act = act;
     for (int l = 0; l < 4; ++l) { p.bias[l] = F(boff[l]); p.inv_ws[l] = IS(l); }
     p.tcol = tcol; p.t_dev = t_dev; p.t_host = t_host; p.y = y;
+    p.dbg = tc_debug_buffer();
     CFM_CUDA_OK(cudaFuncSetAttribute(mlp_fused_h3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFSmemBytes));
     int grid = (batch + kTM - 1) / kTM;
     if (grid > sm_count()) grid = sm_count();

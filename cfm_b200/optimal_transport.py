@@ -402,7 +402,7 @@ class OTPlanSampler:
         if err is not None:
             info["err"] = err
         self._last_info = info
-        if st[0] & _ffi.FLAG_INFEASIBLE:
+        if st[0] & _ffi.FLAG_INFEASIBLE or (cp.method == "exact" and st[0] & _ffi.FLAG_NONFINITE):
             raise RuntimeError("exact OT: the cost matrix has no finite assignment (inf/nan costs)")
         if st[0] & _ffi.FLAG_NONFINITE:
             print("ERROR: p is not finite")
