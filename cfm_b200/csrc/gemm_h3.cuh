@@ -74,6 +74,14 @@ __device__ __forceinline__ void split_h3_sat(float v, __half& hi, __half& lo) {
   lo = f2h_satfinite((v - __half2float(hi)) * kH3Scale);
 }
 
+// two values at once: packed (hi0 | hi1 << 16) and (lo0 | lo1 << 16) via cvt.rn.satfinite.f16x2.f32
+__device__ __forceinline__ void split_h3_sat_x2(float v0, float v1, uint32_t& hi2, uint32_t& lo2) {
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(v1), "f"(v0));  // first source -> upper half
+  const __half2 h = *reinterpret_cast<const __half2*>(&hi2);
+  const float r0 = (v0 - __low2float(h)) * kH3Scale, r1 = (v1 - __high2float(h)) * kH3Scale;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(r1), "f"(r0));
+}
+
 // Epilogue functor interface (called by whole warps, thread = row):
 //   begin_row(row, ok)
 //   store32(row0, lane, col0, const float (&acc)[32], n_rows, n_cols, tile)   acc = acc0 + acc1 * 2^-11

@@ -189,7 +189,10 @@ struct FusedParams {
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+constexpr int kFEpiWarps = 16;                   // four per TMEM lane quadrant, one 32-column chunk each
+constexpr int kFThreads = 64 + 32 * kFEpiWarps;  // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
+
+__global__ void __launch_bounds__(kFThreads, 1)
 mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                     const __grid_constant__ CUtensorMap map_w0h, const __grid_constant__ CUtensorMap map_w0l,
                     const __grid_constant__ CUtensorMap map_w1h, const __grid_constant__ CUtensorMap map_w1l,
@@ -222,8 +225,8 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
     for (int s = 0; s < kFRingStages; ++s) { mbar_init(&r_full[s], 1); mbar_init(&r_empty[s], 1); }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 32 * kEpiWarps);
-      mbar_init(&act_ready[a], 32 * kEpiWarps);
+      mbar_init(&tempty[a], 32 * kFEpiWarps);
+      mbar_init(&act_ready[a], 32 * kFEpiWarps);
     }
     mbar_init(slab_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -361,9 +364,12 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
     // no asynchronous arrive may still be in flight towards this CTA's shared memory when it exits
     if (done_slabs > 0) mbar_wait(slab_done, (uint32_t)((done_slabs - 1) & 1));
   } else {
-    // ===================== epilogue (warps 2..9) =====================
+    // ===================== epilogue (warps 2..17) =====================
+    // 16 warps, four per TMEM lane quadrant; a warp drains ONE 32-column chunk of the 128-column tile (both
+    // accumulators).  The read-out is latency-bound (TMEM load -> dependent math -> stores), so it is the
+    // number of warps in flight, not the instruction count, that sets its duration.
     const int quad = warp & 3;          // TMEM lane quadrant
-    const int half = (warp - 2) >> 2;   // 64-column half of the 128-column tile
+    const int part = (warp - 2) >> 2;   // 32-column chunk of the 128-column tile
     const int r_in = quad * 32 + lane;  // row inside the slab
     uint32_t g = 0;
     for (int slab = blockIdx.x; slab < num_slabs; slab += gridDim.x) {
@@ -380,55 +386,63 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
         }
         tc_fence_after();
         if (warp == 2 && lane == 0 && slab == (int)blockIdx.x && tl < 16) F_MARK(8 + 2 * tl);  // accumulators ready
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + b * 256u + (uint32_t)(half * 64);
-        const float* bias = p.bias[layer - 1];
-        const float* inv_ws = p.inv_ws[layer - 1];
-#pragma unroll 1
-        for (int c0 = 0; c0 < 64; c0 += 32) {
-          uint32_t r0[32], r1[32];
-          tc_ld32_nowait(taddr + c0, r0);
-          tc_ld32_nowait(taddr + 128 + c0, r1);
-          tc_ld_wait();
-          const int col0 = n * 128 + half * 64 + c0;  // column of this layer's output
-          float o[32];
-          if (layer < 4 || col0 + 32 <= p.out_dim) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + b * 256u + (uint32_t)(part * 32);
+        const float* bias = layer == 1 ? p.bias[0] : layer == 2 ? p.bias[1] : layer == 3 ? p.bias[2] : p.bias[3];
+        const float* inv_ws = layer == 1 ? p.inv_ws[0] : layer == 2 ? p.inv_ws[1] : layer == 3 ? p.inv_ws[2] : p.inv_ws[3];
+        uint32_t r0[32], r1[32];
+        tc_ld32_nowait(taddr, r0);
+        tc_ld32_nowait(taddr + 128, r1);
+        const int col0 = n * 128 + part * 32;  // column of this layer's output
+        const bool with_t = layer == 1 && p.tcol != nullptr;
+        tc_ld_wait();
+        if (layer < 4) {
+          // activations -> shared memory, K-major 128B-swizzled operand layout:
+          // chunk kc = col / 64 (16 KB each), row r at r * 128 B, 16-byte unit u stored at u ^ (r & 7)
+          const int kc = col0 >> 6, u0 = (col0 & 63) >> 3;
+          uint8_t* bh = act + kc * kHABytes + r_in * 128;
+          uint8_t* bl = bh + kFActBytes / 2;
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {  // 8 columns = one 16-byte unit of hi and of lo
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int c = 8 * gq + 4 * q;
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col0 + c));
+              const float4 is = __ldg(reinterpret_cast<const float4*>(inv_ws + col0 + c));
+              float a0 = fmaf(__uint_as_float(r1[c]), kH3InvScale, __uint_as_float(r0[c]));
+              float a1 = fmaf(__uint_as_float(r1[c + 1]), kH3InvScale, __uint_as_float(r0[c + 1]));
+              float a2 = fmaf(__uint_as_float(r1[c + 2]), kH3InvScale, __uint_as_float(r0[c + 2]));
+              float a3 = fmaf(__uint_as_float(r1[c + 3]), kH3InvScale, __uint_as_float(r0[c + 3]));
+              a0 = fmaf(a0, is.x, bb.x); a1 = fmaf(a1, is.y, bb.y); a2 = fmaf(a2, is.z, bb.z); a3 = fmaf(a3, is.w, bb.w);
+              if (with_t) {
+                const float4 tc4 = __ldg(reinterpret_cast<const float4*>(p.tcol + col0 + c));
+                a0 = fmaf(t, tc4.x, a0); a1 = fmaf(t, tc4.y, a1); a2 = fmaf(t, tc4.z, a2); a3 = fmaf(t, tc4.w, a3);
+              }
+              v[4 * q] = act_apply_fast(a0, p.act); v[4 * q + 1] = act_apply_fast(a1, p.act);
+              v[4 * q + 2] = act_apply_fast(a2, p.act); v[4 * q + 3] = act_apply_fast(a3, p.act);
+            }
+            uint32_t ph[4], pl[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_h3_sat_x2(v[2 * e], v[2 * e + 1], ph[e], pl[e]);
+            const int off = ((u0 + gq) ^ (r_in & 7)) << 4;
+            *reinterpret_cast<uint4*>(bh + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            *reinterpret_cast<uint4*>(bl + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+          }
+        } else if (row < p.batch) {
+          if (col0 + 32 <= p.out_dim) {
+            float4* dst = reinterpret_cast<float4*>(p.y + (int64_t)row * p.out_dim + col0);
 #pragma unroll
             for (int c = 0; c < 32; c += 4) {
               const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col0 + c));
               const float4 is = __ldg(reinterpret_cast<const float4*>(inv_ws + col0 + c));
-              float4 tc4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (layer == 1 && p.tcol) tc4 = __ldg(reinterpret_cast<const float4*>(p.tcol + col0 + c));
-              const float isv[4] = {is.x, is.y, is.z, is.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
-              const float tv[4] = {tc4.x, tc4.y, tc4.z, tc4.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float acc = fmaf(__uint_as_float(r1[c + e]), kH3InvScale, __uint_as_float(r0[c + e]));
-                float v = fmaf(acc, isv[e], bv[e]);
-                if (layer == 1) v = fmaf(t, tv[e], v);
-                o[c + e] = layer < 4 ? act_apply_fast(v, p.act) : v;
-              }
+              float4 o;
+              o.x = fmaf(fmaf(__uint_as_float(r1[c]), kH3InvScale, __uint_as_float(r0[c])), is.x, bb.x);
+              o.y = fmaf(fmaf(__uint_as_float(r1[c + 1]), kH3InvScale, __uint_as_float(r0[c + 1])), is.y, bb.y);
+              o.z = fmaf(fmaf(__uint_as_float(r1[c + 2]), kH3InvScale, __uint_as_float(r0[c + 2])), is.z, bb.z);
+              o.w = fmaf(fmaf(__uint_as_float(r1[c + 3]), kH3InvScale, __uint_as_float(r0[c + 3])), is.w, bb.w);
+              dst[c >> 2] = o;
             }
-            if (layer < 4) {
-              // activations -> shared memory, K-major 128B-swizzled operand layout:
-              // chunk kc = col / 64 (16 KB each), row r at r * 128 B, 16-byte unit u stored at u ^ (r & 7)
-              const int kc = col0 >> 6, u0 = (col0 & 63) >> 3;
-              uint8_t* bh = act + kc * kHABytes + r_in * 128;
-              uint8_t* bl = bh + kFActBytes / 2;
-#pragma unroll
-              for (int gq = 0; gq < 4; ++gq) {
-                __half hh[8], ll[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) split_h3_sat(o[8 * gq + c], hh[c], ll[c]);
-                const int off = ((u0 + gq) ^ (r_in & 7)) << 4;
-                *reinterpret_cast<uint4*>(bh + off) = pack8(hh);
-                *reinterpret_cast<uint4*>(bl + off) = pack8(ll);
-              }
-            } else if (row < p.batch) {
-              float4* dst = reinterpret_cast<float4*>(p.y + (int64_t)row * p.out_dim + col0);
-#pragma unroll
-              for (int c = 0; c < 8; ++c) dst[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
-            }
-          } else if (row < p.batch) {  // ragged tail of the last layer-4 tile
+          } else {  // ragged tail of the last layer-4 tile
             for (int c = 0; c < 32; ++c)
               if (col0 + c < p.out_dim) {
                 const float acc = fmaf(__uint_as_float(r1[c]), kH3InvScale, __uint_as_float(r0[c]));
@@ -521,7 +535,7 @@ int mlp_tc_forward(const MlpBlobHeader& h, const void* blob, const float* x, con
     CFM_CUDA_OK(cudaFuncSetAttribute(mlp_fused_h3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFSmemBytes));
     int grid = (batch + kTM - 1) / kTM;
     if (grid > sm_count()) grid = sm_count();
-    mlp_fused_h3_kernel<<<grid, kTcThreads, kFSmemBytes, s>>>(mx[0], mx[1], mw[0], mw[1], mw[2], mw[3], mw[4], mw[5],
+    mlp_fused_h3_kernel<<<grid, kFThreads, kFSmemBytes, s>>>(mx[0], mx[1], mw[0], mw[1], mw[2], mw[3], mw[4], mw[5],
                                                               mw[6], mw[7], p);
     ::cfm::note_launches(1);
     CFM_CUDA_OK(cudaGetLastError());

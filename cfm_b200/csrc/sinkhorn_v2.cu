@@ -62,6 +62,10 @@ __device__ __forceinline__ void v2_bulk_load_hint(void* dst, const void* src, ui
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                ::"r"(v2_smem_u32(dst)), "l"(src), "r"(bytes), "r"(v2_smem_u32(bar)), "l"(policy) : "memory");
 }
+// fire-and-forget L2 prefetch of a contiguous global range (no shared memory, no completion tracking)
+__device__ __forceinline__ void v2_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ uint64_t v2_policy_evict_last() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
@@ -212,6 +216,23 @@ __global__ void __launch_bounds__(NT, 512 / NT) sinkhorn_v2_kernel(const SkParam
   };
   if (tid == 0)
     for (int q = 0; q < S; ++q) issue_next();  // initial fill (wraps into the next sweep if S > nchunks)
+  // While the grid sits in the two barriers and the combine between two sweeps (~10 us per iteration) the HBM
+  // is idle except for the refill of the shared-memory ring (S chunks).  Thread 0 uses that window: at the end
+  // of a sweep it prefetches into L2 the p.prefetch_chunks chunks the next sweep will ask for right after the
+  // ones already in the ring, so the sweep starts on L2 hits and the DRAM transfer of those rows overlaps the
+  // barrier latency instead of the streaming phase.  A hint only: results do not depend on it.
+  auto prefetch_ahead = [&]() {
+    int c = p_chunk, dir = p_dir;
+    for (int q = 0; q < p.prefetch_chunks; ++q) {
+      if (c < 0 || c >= nchunks) break;  // the sweep after next is not worth fetching yet
+      if (!(resident >= 0 && c < resident)) {  // resident chunks are L2 hits already
+        const int r0 = r_begin + c * R;
+        const int rv = min(R, r_begin + nrows - r0);
+        for (int r = 0; r < rv; ++r) v2_prefetch_l2(p.M + (int64_t)(r0 + r) * p.ldm, (uint32_t)n1 * 4u);
+      }
+      c += dir;
+    }
+  };
 
   // ---- one fused sweep ----
   auto sweep = [&](bool do_row, bool do_col, const float* v_cur) {
@@ -336,6 +357,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) sinkhorn_v2_kernel(const SkParam
       }
       consumed_total += nchunks;
       ++sweep_no;
+      if (tid == 0) prefetch_ahead();
       if (do_col) {
         // sum_i ex2(M c2 + u_i) over this slab = cs * 2^(kappa + uref): partial (max, sum) form
         const float pm = kappa + uref;
@@ -440,6 +462,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) sinkhorn_v2_kernel(const SkParam
     }
     consumed_total += nchunks;
     ++sweep_no;
+    if (tid == 0) prefetch_ahead();
     if (do_col) {
 #pragma unroll
       for (int k = 0; k < KG; ++k)
@@ -620,6 +643,9 @@ int sinkhorn_v2_launch(SkParams& p, cudaStream_t s) {
   static int dbg = -1;  // CFM_SK_DBG: A/B switches (bit0: 4-wide combine loads, bit1: marginal error every iteration)
   if (dbg < 0) { const char* e = getenv("CFM_SK_DBG"); dbg = e ? atoi(e) : 1; }  // same-box A/B: 4-wide loads 45.6 us/iter, 8-wide 45.9, error every iteration +0.9
   p.dbg_flags = dbg;
+  static int pf = -1;  // CFM_SK_PF: chunks (of R rows) per CTA prefetched into L2 at the end of every sweep
+  if (pf < 0) { const char* e = getenv("CFM_SK_PF"); pf = e ? atoi(e) : 6; }
+  p.prefetch_chunks = ((size_t)p.n0 * p.n1 * 4 > (size_t)100 << 20) ? pf : 0;  // pointless when M lives in L2 anyway
   static int cfg = -1;  // CFM_SK_CONFIG: 0 heuristic (default), 1 force 512-thread CTAs, 2 force 256-thread CTAs
   if (cfg < 0) { const char* e = getenv("CFM_SK_CONFIG"); cfg = e ? atoi(e) : 0; }
   const int ng = p.n1p / 4;

@@ -35,7 +35,8 @@ struct SqDistEpilogue {
   float tmax;
 
   __device__ __forceinline__ float one(float dot, float a, float b) {
-    float v = fmaxf((a + b) - 2.f * dot, 0.f);
+    const float d2 = (a + b) - 2.f * dot;
+    float v = d2 < 0.f ? 0.f : d2;  // clamp_min(0) that lets NaN through, like ATen's (fmaxf would swallow it)
     float r = __fsqrt_rn(v);
     return squared ? r * r : r;
   }

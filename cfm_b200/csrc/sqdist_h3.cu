@@ -78,8 +78,12 @@ struct SqDistH3Epilogue {
   }
   __device__ __forceinline__ float one(float acc, float b, float ib) const {
     const float dot = (acc * ia) * ib;  // exact rescale
-    const float v = fmaxf((a + b) - 2.f * dot, 0.f);
-    const float s = __fsqrt_rn(v);
+    const float d2 = (a + b) - 2.f * dot;
+    const float v = d2 < 0.f ? 0.f : d2;  // clamp_min(0) that lets NaN through, like ATen's
+    // sqrt-then-square mimics cdist(...)**2; on this path the contraction itself is good to ~1e-6 of the norms,
+    // so the 2-ulp approximate square root (one MUFU, no IEEE fix-up subroutine) does not show
+    float s;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(v));
     return squared ? s * s : s;
   }
   __device__ __forceinline__ void store32(int row0, int lane, int col0, const float (&r)[32], int n0, int n1,

@@ -31,7 +31,8 @@ struct SqDistTcEpilogue {
   float a, tmax;
   __device__ __forceinline__ void begin_row(int row, bool ok) { a = ok ? __ldg(nx + row) : 0.f; }
   __device__ __forceinline__ float one(float acc, float b) {
-    float v = fmaxf((a + b) - 2.f * acc, 0.f);
+    const float d2 = (a + b) - 2.f * acc;
+    float v = d2 < 0.f ? 0.f : d2;  // clamp_min(0) that lets NaN through, like ATen's
     const float s = __fsqrt_rn(v);
     return squared ? s * s : s;
   }

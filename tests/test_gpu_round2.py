@@ -40,9 +40,10 @@ def test_cost_matrix_fp16x3_vs_simt_and_cdist(n0, n1, d):
     assert (h3 - simt).abs().max().item() <= 2.5e-6 * scale
     assert (h3 - ref).abs().max().item() <= 2.5e-6 * scale
     assert cmax == h3.max().item() and (h3 >= 0).all()
-    sk = OTPlanSampler("sinkhorn")  # auto mode (cost_algo=0) of a Sinkhorn sampler = the fp16x3 path for these shapes
-    Ma, _, _, _ = sk._cost(x0.to(DEV), x1.to(DEV), torch.device(DEV))
-    assert torch.equal(Ma[:, :n1].cpu(), h3)
+    if n0 * n1 >= 256 * 256:  # auto mode (cost_algo=0) of a Sinkhorn sampler = the fp16x3 path from this size on
+        sk = OTPlanSampler("sinkhorn")
+        Ma, _, _, _ = sk._cost(x0.to(DEV), x1.to(DEV), torch.device(DEV))
+        assert torch.equal(Ma[:, :n1].cpu(), h3)
     un, _ = gpu_cost(x0, x1, squared=False, algo=3)
     assert (un - torch.cdist(x0, x1)).abs().max().item() <= 1e-5 * max(1.0, ref.max().sqrt().item())
 
