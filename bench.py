@@ -265,7 +265,7 @@ def main():
 
     # nvidia-smi is started BEFORE the warm-up (its start-up stalls the GPU for a few ms) and keeps
     # sampling through the timed region
-    clocks = ClockSampler(local_rank) if rank == 0 else None
+    clocks = ClockSampler(local_rank) if (rank == 0 and not os.environ.get("CFM_BENCH_NOCLK")) else None
     if clocks is not None:
         time.sleep(0.7)  # let nvidia-smi finish initialising NVML before any timed work
     for _ in range(args.warmup):

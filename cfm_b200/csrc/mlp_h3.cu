@@ -430,17 +430,31 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
           }
         } else if (row < p.batch) {
           if (col0 + 32 <= p.out_dim) {
-            float4* dst = reinterpret_cast<float4*>(p.y + (int64_t)row * p.out_dim + col0);
+            // thread = row: its 32 outputs are 128 contiguous bytes.  256-bit stores (one full 32-byte sector per
+            // instruction) when the row is 32-byte aligned, 128-bit ones otherwise.
+            float* dst = p.y + (int64_t)row * p.out_dim + col0;
+            const bool wide = ((reinterpret_cast<uintptr_t>(dst) & 31) == 0);
 #pragma unroll
-            for (int c = 0; c < 32; c += 4) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col0 + c));
-              const float4 is = __ldg(reinterpret_cast<const float4*>(inv_ws + col0 + c));
-              float4 o;
-              o.x = fmaf(fmaf(__uint_as_float(r1[c]), kH3InvScale, __uint_as_float(r0[c])), is.x, bb.x);
-              o.y = fmaf(fmaf(__uint_as_float(r1[c + 1]), kH3InvScale, __uint_as_float(r0[c + 1])), is.y, bb.y);
-              o.z = fmaf(fmaf(__uint_as_float(r1[c + 2]), kH3InvScale, __uint_as_float(r0[c + 2])), is.z, bb.z);
-              o.w = fmaf(fmaf(__uint_as_float(r1[c + 3]), kH3InvScale, __uint_as_float(r0[c + 3])), is.w, bb.w);
-              dst[c >> 2] = o;
+            for (int c = 0; c < 32; c += 8) {
+              float o[8];
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col0 + c + 4 * q));
+                const float4 is = __ldg(reinterpret_cast<const float4*>(inv_ws + col0 + c + 4 * q));
+                const int e = c + 4 * q;
+                o[4 * q] = fmaf(fmaf(__uint_as_float(r1[e]), kH3InvScale, __uint_as_float(r0[e])), is.x, bb.x);
+                o[4 * q + 1] = fmaf(fmaf(__uint_as_float(r1[e + 1]), kH3InvScale, __uint_as_float(r0[e + 1])), is.y, bb.y);
+                o[4 * q + 2] = fmaf(fmaf(__uint_as_float(r1[e + 2]), kH3InvScale, __uint_as_float(r0[e + 2])), is.z, bb.z);
+                o[4 * q + 3] = fmaf(fmaf(__uint_as_float(r1[e + 3]), kH3InvScale, __uint_as_float(r0[e + 3])), is.w, bb.w);
+              }
+              if (wide) {
+                asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + c), "f"(o[0]), "f"(o[1]),
+                             "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
+                             : "memory");
+              } else {
+                *reinterpret_cast<float4*>(dst + c) = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4*>(dst + c + 4) = make_float4(o[4], o[5], o[6], o[7]);
+              }
             }
           } else {  // ragged tail of the last layer-4 tile
             for (int c = 0; c < 32; ++c)

@@ -644,7 +644,9 @@ int sinkhorn_v2_launch(SkParams& p, cudaStream_t s) {
   if (dbg < 0) { const char* e = getenv("CFM_SK_DBG"); dbg = e ? atoi(e) : 1; }  // same-box A/B: 4-wide loads 45.6 us/iter, 8-wide 45.9, error every iteration +0.9
   p.dbg_flags = dbg;
   static int pf = -1;  // CFM_SK_PF: chunks (of R rows) per CTA prefetched into L2 at the end of every sweep
-  if (pf < 0) { const char* e = getenv("CFM_SK_PF"); pf = e ? atoi(e) : 6; }
+  // measured on B200 at C2 (same box, 10 steps each): 0 -> 4.53 ms, 3 -> 4.60, 6 -> 4.76, 10 -> 5.16, 14 -> 5.61:
+  // the prefetched rows displace the evict_last resident part of the slabs from L2, so the default is off
+  if (pf < 0) { const char* e = getenv("CFM_SK_PF"); pf = e ? atoi(e) : 0; }
   p.prefetch_chunks = ((size_t)p.n0 * p.n1 * 4 > (size_t)100 << 20) ? pf : 0;  // pointless when M lives in L2 anyway
   static int cfg = -1;  // CFM_SK_CONFIG: 0 heuristic (default), 1 force 512-thread CTAs, 2 force 256-thread CTAs
   if (cfg < 0) { const char* e = getenv("CFM_SK_CONFIG"); cfg = e ? atoi(e) : 0; }

@@ -380,13 +380,23 @@ class OTPlanSampler:
         sync -- or, for ``defer`` (Sinkhorn calls of a warn=False sampler, whose conditions only print),
         once its copy to pinned memory has landed: at the next call or when ``last_info`` is read."""
         if defer:
-            pinned = torch.empty(4, dtype=torch.int32, pin_memory=True)
+            # pinned landing slots are allocated ONCE (a fresh pinned block is a cudaHostAlloc, which waits for
+            # the device to go idle and would drain the launch queue in the middle of a training loop)
+            ring = self.__dict__.get("_status_ring")
+            if ring is None:
+                ring = self._status_ring = {"k": 0, "buf": torch.empty((16, 4), dtype=torch.int32, pin_memory=True)}
+            while len(self._pending) >= 12:  # a slot is reused only after its status word has been evaluated
+                self._flush_pending(block=False)
+                if len(self._pending) >= 12:
+                    ev0, pinned0, cp0 = self._pending.popleft()
+                    ev0.synchronize()
+                    self._evaluate_status(cp0, pinned0.tolist(), None)
+            pinned = ring["buf"][ring["k"]]
+            ring["k"] = (ring["k"] + 1) % 16
             pinned.copy_(cp.status, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(cp.status.device))
             self._pending.append((ev, pinned, cp))
-            while len(self._pending) > 8:
-                self._flush_pending(block=True)
             return None
         self._flush_pending(block=True)
         st = cp.status.cpu().tolist()
