@@ -379,6 +379,20 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
         const int layer = tl < 6 ? (tl >> 1) + 1 : 4;
         const int n = tl < 6 ? (tl & 1) : tl - 6;
         const uint32_t b = g & 1;
+        const float* bias = layer == 1 ? p.bias[0] : layer == 2 ? p.bias[1] : layer == 3 ? p.bias[2] : p.bias[3];
+        const float* inv_ws = layer == 1 ? p.inv_ws[0] : layer == 2 ? p.inv_ws[1] : layer == 3 ? p.inv_ws[2] : p.inv_ws[3];
+        const int col0 = n * 128 + part * 32;  // column of this layer's output
+        // Per-column constants of this warp's 32 columns: lane l fetches column col0 + l (one coalesced 128-byte
+        // load per array) BEFORE waiting for the accumulators, and the unrolled math broadcasts them with
+        // shuffles.  With 224 KB of shared memory in use the L1 is a few KB, so loads issued next to their use
+        // would each pay an L2 round trip on the read-out's critical path.
+        const int ncols = layer < 4 ? kFW : p.out_dim;
+        float bias_l = 0.f, is_l = 0.f;
+        if (col0 + lane < ncols) {
+          bias_l = __ldg(bias + col0 + lane);
+          is_l = __ldg(inv_ws + col0 + lane);
+          if (layer == 1 && p.tcol != nullptr) bias_l = fmaf(t, __ldg(p.tcol + col0 + lane), bias_l);  // + t * W0[:, -1]
+        }
         mbar_wait(&tfull[b], (g >> 1) & 1);
         if (layer < 4 && n == 0) {
           // this layer's other tile still reads the activations this epilogue is about to overwrite
@@ -387,14 +401,12 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
         tc_fence_after();
         if (warp == 2 && lane == 0 && slab == (int)blockIdx.x && tl < 16) F_MARK(8 + 2 * tl);  // accumulators ready
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + b * 256u + (uint32_t)(part * 32);
-        const float* bias = layer == 1 ? p.bias[0] : layer == 2 ? p.bias[1] : layer == 3 ? p.bias[2] : p.bias[3];
-        const float* inv_ws = layer == 1 ? p.inv_ws[0] : layer == 2 ? p.inv_ws[1] : layer == 3 ? p.inv_ws[2] : p.inv_ws[3];
         uint32_t r0[32], r1[32];
         tc_ld32_nowait(taddr, r0);
         tc_ld32_nowait(taddr + 128, r1);
-        const int col0 = n * 128 + part * 32;  // column of this layer's output
-        const bool with_t = layer == 1 && p.tcol != nullptr;
         tc_ld_wait();
+#define F_BIAS(c) __shfl_sync(0xffffffffu, bias_l, (c))
+#define F_IS(c) __shfl_sync(0xffffffffu, is_l, (c))
         if (layer < 4) {
           // activations -> shared memory, K-major 128B-swizzled operand layout:
           // chunk kc = col / 64 (16 KB each), row r at r * 128 B, 16-byte unit u stored at u ^ (r & 7)
@@ -407,17 +419,12 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
               const int c = 8 * gq + 4 * q;
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col0 + c));
-              const float4 is = __ldg(reinterpret_cast<const float4*>(inv_ws + col0 + c));
               float a0 = fmaf(__uint_as_float(r1[c]), kH3InvScale, __uint_as_float(r0[c]));
               float a1 = fmaf(__uint_as_float(r1[c + 1]), kH3InvScale, __uint_as_float(r0[c + 1]));
               float a2 = fmaf(__uint_as_float(r1[c + 2]), kH3InvScale, __uint_as_float(r0[c + 2]));
               float a3 = fmaf(__uint_as_float(r1[c + 3]), kH3InvScale, __uint_as_float(r0[c + 3]));
-              a0 = fmaf(a0, is.x, bb.x); a1 = fmaf(a1, is.y, bb.y); a2 = fmaf(a2, is.z, bb.z); a3 = fmaf(a3, is.w, bb.w);
-              if (with_t) {
-                const float4 tc4 = __ldg(reinterpret_cast<const float4*>(p.tcol + col0 + c));
-                a0 = fmaf(t, tc4.x, a0); a1 = fmaf(t, tc4.y, a1); a2 = fmaf(t, tc4.z, a2); a3 = fmaf(t, tc4.w, a3);
-              }
+              a0 = fmaf(a0, F_IS(c), F_BIAS(c)); a1 = fmaf(a1, F_IS(c + 1), F_BIAS(c + 1));
+              a2 = fmaf(a2, F_IS(c + 2), F_BIAS(c + 2)); a3 = fmaf(a3, F_IS(c + 3), F_BIAS(c + 3));
               v[4 * q] = act_apply_fast(a0, p.act); v[4 * q + 1] = act_apply_fast(a1, p.act);
               v[4 * q + 2] = act_apply_fast(a2, p.act); v[4 * q + 3] = act_apply_fast(a3, p.act);
             }
@@ -428,7 +435,9 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
             *reinterpret_cast<uint4*>(bh + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
             *reinterpret_cast<uint4*>(bl + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
           }
-        } else if (row < p.batch) {
+        } else {
+          // (shuffles below are executed by the whole warp; only the stores are predicated on the row being valid)
+          const bool row_ok = row < p.batch;
           if (col0 + 32 <= p.out_dim) {
             // thread = row: its 32 outputs are 128 contiguous bytes.  256-bit stores (one full 32-byte sector per
             // instruction) when the row is 32-byte aligned, 128-bit ones otherwise.
@@ -438,32 +447,31 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
             for (int c = 0; c < 32; c += 8) {
               float o[8];
 #pragma unroll
-              for (int q = 0; q < 2; ++q) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col0 + c + 4 * q));
-                const float4 is = __ldg(reinterpret_cast<const float4*>(inv_ws + col0 + c + 4 * q));
-                const int e = c + 4 * q;
-                o[4 * q] = fmaf(fmaf(__uint_as_float(r1[e]), kH3InvScale, __uint_as_float(r0[e])), is.x, bb.x);
-                o[4 * q + 1] = fmaf(fmaf(__uint_as_float(r1[e + 1]), kH3InvScale, __uint_as_float(r0[e + 1])), is.y, bb.y);
-                o[4 * q + 2] = fmaf(fmaf(__uint_as_float(r1[e + 2]), kH3InvScale, __uint_as_float(r0[e + 2])), is.z, bb.z);
-                o[4 * q + 3] = fmaf(fmaf(__uint_as_float(r1[e + 3]), kH3InvScale, __uint_as_float(r0[e + 3])), is.w, bb.w);
-              }
-              if (wide) {
-                asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + c), "f"(o[0]), "f"(o[1]),
-                             "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
-                             : "memory");
-              } else {
-                *reinterpret_cast<float4*>(dst + c) = make_float4(o[0], o[1], o[2], o[3]);
-                *reinterpret_cast<float4*>(dst + c + 4) = make_float4(o[4], o[5], o[6], o[7]);
+              for (int q = 0; q < 8; ++q)
+                o[q] = fmaf(fmaf(__uint_as_float(r1[c + q]), kH3InvScale, __uint_as_float(r0[c + q])), F_IS(c + q),
+                            F_BIAS(c + q));
+              if (row_ok) {
+                if (wide) {
+                  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + c), "f"(o[0]),
+                               "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
+                               : "memory");
+                } else {
+                  *reinterpret_cast<float4*>(dst + c) = make_float4(o[0], o[1], o[2], o[3]);
+                  *reinterpret_cast<float4*>(dst + c + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                }
               }
             }
           } else {  // ragged tail of the last layer-4 tile
-            for (int c = 0; c < 32; ++c)
-              if (col0 + c < p.out_dim) {
-                const float acc = fmaf(__uint_as_float(r1[c]), kH3InvScale, __uint_as_float(r0[c]));
-                p.y[(int64_t)row * p.out_dim + col0 + c] = fmaf(acc, __ldg(inv_ws + col0 + c), __ldg(bias + col0 + c));
-              }
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float acc = fmaf(__uint_as_float(r1[c]), kH3InvScale, __uint_as_float(r0[c]));
+              const float o = fmaf(acc, F_IS(c), F_BIAS(c));
+              if (row_ok && col0 + c < p.out_dim) p.y[(int64_t)row * p.out_dim + col0 + c] = o;
+            }
           }
         }
+#undef F_BIAS
+#undef F_IS
         tc_fence_before();
         mbar_arrive(&tempty[b]);
         if (layer < 4) {
