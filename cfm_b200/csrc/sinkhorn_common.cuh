@@ -42,6 +42,7 @@ struct SkParams {
   int v_in_smem;
   float l2_resident_frac;  // sinkhorn_v2: share of each slab loaded with L2 evict_last (0: default policy)
   int dbg_flags;    // sinkhorn_v2 A/B switches (CFM_SK_DBG)
+  int atomic_cols;      // sinkhorn_v2, factored regime: reduce the column partials with fixed-point atomics (one barrier per sweep)
   int prefetch_chunks;  // sinkhorn_v2: row chunks per CTA prefetched into L2 during the inter-sweep barriers
   int run_if;       // 0 always; 1 only when auto-mode resolves to fast; 2 only when it resolves to precise
   int mixed;        // precise mode only: float64 potentials and exponent ARGUMENTS, fp32 exponentials (see expd)

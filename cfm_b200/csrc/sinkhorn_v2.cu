@@ -235,10 +235,15 @@ __global__ void __launch_bounds__(NT, 512 / NT) sinkhorn_v2_kernel(const SkParam
   };
 
   // ---- one fused sweep ----
-  auto sweep = [&](bool do_row, bool do_col, const float* v_cur) {
+  // v_in (single-barrier mode): this thread's columns of v in registers and the common reference vref_in;
+  // acc_out (single-barrier mode): fixed-point column accumulator the partials are added to
+  // v_reload (single-barrier mode): where this thread parked its v before the sweep (re-read for the partial scaling
+  // at the end, so that 16 registers do not stay live across the streaming loop); null = v is zero (prologue)
+  auto sweep = [&](bool do_row, bool do_col, const float* v_cur, const float4* v_in, float vref_in,
+                   unsigned long long* acc_out, const float* v_reload) {
     if (fact) {
       // ---------------- factored (kernel-space in registers) sweep ----------------
-      const float vref = do_row ? __ldcg(v_cur) : 0.f;
+      const float vref = do_row ? (v_in ? vref_in : __ldcg(v_cur)) : 0.f;
       const float nkap = -kappa;
       float4 V[kVSmem ? 1 : KG];
       float cs[KG][4];
@@ -247,7 +252,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) sinkhorn_v2_kernel(const SkParam
         float4 vk = make_float4(0.f, 0.f, 0.f, 0.f);  // idle columns: weight 0
         if (gvalid[k]) {
           if (do_row) {
-            const float4 vv = __ldcg(reinterpret_cast<const float4*>(v_cur + tcol + kV2Consumers * 4 * k));
+            const float4 vv = v_in ? v_in[k]
+                                   : __ldcg(reinterpret_cast<const float4*>(v_cur + tcol + kV2Consumers * 4 * k));
             vk = make_float4(ex2f(vv.x - vref), ex2f(vv.y - vref), ex2f(vv.z - vref), ex2f(vv.w - vref));
           } else {
             vk = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -358,7 +364,26 @@ __global__ void __launch_bounds__(NT, 512 / NT) sinkhorn_v2_kernel(const SkParam
       consumed_total += nchunks;
       ++sweep_no;
       if (tid == 0) prefetch_ahead();
-      if (do_col) {
+      if (do_col && acc_out != nullptr) {
+        // Single-barrier mode.  Column sum C_j = sum_b cs_bj 2^(kappa + uref_b) and v_new_j = logb - log2 C_j, so
+        // with q_bj = cs_bj 2^(kappa + uref_b + v_j - logb):  sum_b q_bj = 2^(v_j - v_new_j)  (= 1 at the fixed
+        // point).  The q's are added as 32.32 fixed-point integers: integer addition is associative, so the
+        // total -- unlike a floating-point atomic sum -- does not depend on the arrival order of the CTAs.
+        const float sh = kappa + uref - logb;
+#pragma unroll
+        for (int k = 0; k < KG; ++k)
+          if (gvalid[k]) {
+            const float4 vv = v_reload ? __ldcg(reinterpret_cast<const float4*>(v_reload + tcol + kV2Consumers * 4 * k))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float vq[4] = {vv.x, vv.y, vv.z, vv.w};
+            unsigned long long* dst = acc_out + tcol + kV2Consumers * 4 * k;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float q = cs[k][c] * ex2f(sh + vq[c]) * 4294967296.f;
+              atomicAdd(dst + c, (unsigned long long)__float2ll_rn(fminf(fmaxf(q, 0.f), 4.0e18f)));
+            }
+          }
+      } else if (do_col) {
         // sum_i ex2(M c2 + u_i) over this slab = cs * 2^(kappa + uref): partial (max, sum) form
         const float pm = kappa + uref;
 #pragma unroll
@@ -554,19 +579,106 @@ __global__ void __launch_bounds__(NT, 512 / NT) sinkhorn_v2_kernel(const SkParam
 
   // ---- prologue: v^0 from u = 0 ----
   if (b == 0 && tid < 4) p.err_ring[tid] = 0.0;
-  sweep(false, true, nullptr);
-  grid_sync();
-  combine(nullptr, v_work[0], false, nullptr);
-  grid_sync();
 
   int cur = 0, iters = 0;
   bool converged = false;
   double err = 1.0, prev_check_err = -1.0;
+  const bool single = fact && p.atomic_cols != 0;
+  if (single) {
+    // ---- single-barrier iteration: column partials reduced by fixed-point atomics, ONE grid barrier per sweep ----
+    // acc[3][n1p] (zeroed by the launcher) lives in the part_s workspace; sweep s adds into acc[s % 3], after the
+    // barrier every thread reads the totals of ITS columns and forms v_new itself (no combine phase, no second
+    // barrier); buffer (s + 2) % 3 -- last read one barrier ago -- is zeroed by slices for the sweep after next.
+    // v is kept per CTA in the part_m workspace row b (each thread re-reads only what it wrote).
+    unsigned long long* acc = reinterpret_cast<unsigned long long*>(p.part_s);
+    float* vmine = part_m + (int64_t)b * n1p;
+    // v used by the sweep that produced the totals being absorbed lives in vmine (this thread's own columns)
+#pragma unroll
+    for (int k = 0; k < KG; ++k)
+      if (gvalid[k]) *reinterpret_cast<float4*>(vmine + tcol + kV2Consumers * 4 * k) = make_float4(0.f, 0.f, 0.f, 0.f);
+    float vref_cur = 0.f;
+    const int cpc = ((n1 + nblk - 1) / nblk + 3) & ~3;
+    sweep(false, true, nullptr, nullptr, 0.f, acc, nullptr);
+    grid_sync();
+    for (int it = 0;; ++it) {
+      const unsigned long long* tot = acc + (size_t)(it % 3) * n1p;
+      {  // zero this CTA's slice of the buffer of sweep it + 2
+        unsigned long long* z = acc + (size_t)((it + 2) % 3) * n1p;
+        for (int j = b * cpc + tid; j < min(n1, (b + 1) * cpc); j += kV2Threads) z[j] = 0ull;
+      }
+      // totals t_j = 2^(v_j - v_new_j) of this thread's columns (and of column 0, the common reference)
+      float4 vnew[KG];
+      double e2 = 0.0;
+      const float t0 = (float)((double)__ldcg(tot) * 2.3283064365386963e-10);
+      const float vref_new = vref_cur - lg2_abs(t0);
+#pragma unroll
+      for (int k = 0; k < KG; ++k) {
+        float4 vcur_k = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gvalid[k]) vcur_k = __ldcg(reinterpret_cast<const float4*>(vmine + tcol + kV2Consumers * 4 * k));
+        vnew[k] = vcur_k;
+        if (gvalid[k]) {
+          const ulonglong2 a = __ldcg(reinterpret_cast<const ulonglong2*>(tot + tcol + kV2Consumers * 4 * k));
+          const ulonglong2 c = __ldcg(reinterpret_cast<const ulonglong2*>(tot + tcol + kV2Consumers * 4 * k + 2));
+          const double td[4] = {(double)a.x * 2.3283064365386963e-10, (double)a.y * 2.3283064365386963e-10,
+                                (double)c.x * 2.3283064365386963e-10, (double)c.y * 2.3283064365386963e-10};
+          vnew[k] = make_float4(vcur_k.x - lg2_abs((float)td[0]), vcur_k.y - lg2_abs((float)td[1]),
+                                vcur_k.z - lg2_abs((float)td[2]), vcur_k.w - lg2_abs((float)td[3]));
+#pragma unroll
+          for (int q = 0; q < 4; ++q) e2 += (td[q] - 1.0) * (td[q] - 1.0);
+        }
+      }
+      // stopping rule of iteration it - 1 (POT: every check_every iterations, column marginal of (u, v) in L2 norm):
+      // expm1(v_prev - v_new) = t - 1.  Every CTA evaluates it on the same numbers in the same order.
+      if (it >= 1 && (((it - 1) % p.check_every) == 0 || (p.dbg_flags & 2))) {
+        e2 = warp_sum(e2);
+        if (lane == 0) red[warp] = e2;
+        __syncthreads();
+        double t = 0.0;
+        for (int w = 0; w < kV2Warps; ++w) t += red[w];
+        __syncthreads();
+        err = sqrt(t) / (double)n1;
+        if (((it - 1) % p.check_every) == 0) {
+          if (err < p.stop_thr) { converged = true; break; }
+          if (p.stall_tol > 0.0 && prev_check_err >= 0.0 && err > (1.0 - p.stall_tol) * prev_check_err &&
+              err * sqrt((double)n1) < 1e-5) { converged = true; break; }
+          prev_check_err = err;
+        }
+      }
+      if (it == p.max_iters) break;  // (only reached when the last iteration ran its column phase for a check)
+#pragma unroll
+      for (int k = 0; k < KG; ++k)
+        if (gvalid[k]) *reinterpret_cast<float4*>(vmine + tcol + kV2Consumers * 4 * k) = vnew[k];
+      vref_cur = vref_new;
+      const bool last = (it == p.max_iters - 1);
+      const bool check = (it % p.check_every) == 0;
+      const bool do_col = !last || check;
+      sweep(true, do_col, nullptr, vnew, vref_cur, do_col ? acc + (size_t)((it + 1) % 3) * n1p : nullptr, vmine);
+      iters = it + 1;
+      if (!do_col) break;
+      grid_sync();
+    }
+    // outputs: v of the last sweep (parked in vmine by this very thread), u written by the sweep
+    if (b == 0) {
+#pragma unroll
+      for (int k = 0; k < KG; ++k)
+        if (gvalid[k]) {
+          const int j = tcol + kV2Consumers * 4 * k;
+          const float4 vv = __ldcg(reinterpret_cast<const float4*>(vmine + j));
+          p.log_v[j] = (double)vv.x * kLn2d; p.log_v[j + 1] = (double)vv.y * kLn2d;
+          p.log_v[j + 2] = (double)vv.z * kLn2d; p.log_v[j + 3] = (double)vv.w * kLn2d;
+        }
+    }
+  } else {
+  sweep(false, true, nullptr, nullptr, 0.f, nullptr, nullptr);
+  grid_sync();
+  combine(nullptr, v_work[0], false, nullptr);
+  grid_sync();
+
   for (int it = 0; it < p.max_iters; ++it) {
     const bool last = (it == p.max_iters - 1);
     const bool check = (it % p.check_every) == 0;
     const bool do_col = !last || check;
-    sweep(true, do_col, v_work[cur]);
+    sweep(true, do_col, v_work[cur], nullptr, 0.f, nullptr, nullptr);
     iters = it + 1;
     if (!do_col) break;
     grid_sync();
@@ -584,6 +696,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) sinkhorn_v2_kernel(const SkParam
     if (last) break;
     cur ^= 1;
   }
+  }  // two-barrier path
 
   // ---- drain speculative prefetches so no bulk copy is in flight when the CTA exits ----
   if (tid == 0) {
@@ -593,8 +706,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) sinkhorn_v2_kernel(const SkParam
     }
   }
 
-  for (int j = b * kV2Threads + tid; j < n1; j += nblk * kV2Threads)
-    p.log_v[j] = (double)__ldcg(v_work[cur] + j) * kLn2d;
+  if (!single)
+    for (int j = b * kV2Threads + tid; j < n1; j += nblk * kV2Threads)
+      p.log_v[j] = (double)__ldcg(v_work[cur] + j) * kLn2d;
   if (b == 0 && tid == 0) {
     int flags = 0;
     if (!converged) flags |= CFM_FLAG_NOT_CONVERGED;
@@ -602,7 +716,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) sinkhorn_v2_kernel(const SkParam
     p.status[0] = flags;
     p.status[1] = iters;
     p.status[2] = 0;
-    p.status[3] = fact ? 3 : 2;  // kernel variant: 3 = factored sweep, 2 = log-domain sweep
+    p.status[3] = fact ? (single ? 4 : 3) : 2;  // kernel variant: 4 = factored + single barrier, 3 = factored, 2 = log-domain
     *p.err_out = err;
   }
 }
@@ -628,6 +742,8 @@ static int v2_launch_t(SkParams& p, cudaStream_t s) {
   if (grid > p.n0) grid = p.n0;
   void* args[] = {(void*)&p, (void*)&S};
   CFM_CUDA_OK(cudaMemsetAsync(p.err_ring + 4, 0, 16, s));  // grid-barrier counter
+  if (p.atomic_cols)  // the three fixed-point column accumulators of the single-barrier mode
+    CFM_CUDA_OK(cudaMemsetAsync(p.part_s, 0, (size_t)3 * p.n1p * sizeof(unsigned long long), s));
   CFM_CUDA_OK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(NT), args, smem, s));
   note_launches(1);
   return CFM_OK;
@@ -648,6 +764,15 @@ int sinkhorn_v2_launch(SkParams& p, cudaStream_t s) {
   // the prefetched rows displace the evict_last resident part of the slabs from L2, so the default is off
   if (pf < 0) { const char* e = getenv("CFM_SK_PF"); pf = e ? atoi(e) : 0; }
   p.prefetch_chunks = ((size_t)p.n0 * p.n1 * 4 > (size_t)100 << 20) ? pf : 0;  // pointless when M lives in L2 anyway
+  static int atom = -1;  // CFM_SK_ATOMIC: 1 = single-barrier iteration (fixed-point atomic column sums), 0 = two barriers + combine
+  if (atom < 0) { const char* e = getenv("CFM_SK_ATOMIC"); atom = e ? atoi(e) : 1; }
+  p.atomic_cols = atom;
+  static long persist = -2;  // CFM_SK_PERSIST_MB: raise cudaLimitPersistingL2CacheSize before the first solve (experiment)
+  if (persist == -2) {
+    const char* e = getenv("CFM_SK_PERSIST_MB");
+    persist = e ? atol(e) : -1;
+    if (persist >= 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)persist << 20);
+  }
   static int cfg = -1;  // CFM_SK_CONFIG: 0 heuristic (default), 1 force 512-thread CTAs, 2 force 256-thread CTAs
   if (cfg < 0) { const char* e = getenv("CFM_SK_CONFIG"); cfg = e ? atoi(e) : 0; }
   const int ng = p.n1p / 4;
