@@ -15,6 +15,7 @@ stream).  Rank 0 prints ONE JSON line; besides the contract's keys it carries su
 configs (c1_coupling, c4, c5, ode, ode_c1, ode_strong), each with its parity gate.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -268,22 +269,29 @@ def main():
     clocks = ClockSampler(local_rank) if (rank == 0 and not os.environ.get("CFM_BENCH_NOCLK")) else None
     if clocks is not None:
         time.sleep(0.7)  # let nvidia-smi finish initialising NVML before any timed work
+    out = None
     for _ in range(args.warmup):
-        step()
+        out = step()  # results stay alive for one step, as in the timed loop: the allocator's pools reach steady state
     barrier()
 
     # ---- timed region: K steps, device events, barrier + synchronize both sides ----
     sampler.stage_events = []
     launches0 = L.cfm_launch_count()
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    host_ms = []
+    gc.collect()
+    gc.disable()  # no collector pause inside the timed region (it is re-enabled right after)
     barrier()
     marks[0].record()
     for k in range(args.steps):
+        th = time.perf_counter()
         out = step()
         marks[k + 1].record()
+        host_ms.append((time.perf_counter() - th) * 1e3)
     while pending:
         pending.pop(0).wait()
     barrier()
+    gc.enable()
     elapsed_ms = marks[0].elapsed_time(marks[-1])
     per_step = [marks[k].elapsed_time(marks[k + 1]) for k in range(args.steps)]
     launches = L.cfm_launch_count() - launches0
@@ -379,7 +387,9 @@ def main():
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         "parity": parity,
         "step_ms": {"median": float(np.median(per_step)), "min": float(min(per_step)), "max": float(max(per_step)),
-                    "note": "per-step device time of rank 0 (events between steps)"},
+                    "host_enqueue_ms_max": float(max(host_ms)), "host_enqueue_ms_median": float(np.median(host_ms)),
+                    "note": "per-step device time of rank 0 (events between steps); host_enqueue_ms = wall time the host "
+                            "spent inside each (asynchronous) sample_plan call"},
     }
 
     # ---- the other BASELINE configs, each with its parity gate (rank-local work; max over ranks reported) ----

@@ -329,6 +329,9 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
           mbar_wait(&tempty[b], ((g >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t d0 = tmem_base + b * 256u, d1 = d0 + 128u;
+          // the last layer-4 tile may be ragged (784 = 6 x 128 + 16): issue MMAs only as wide as it needs (N % 16 == 0)
+          const int n_cols = layer < 4 ? 128 : min(128, (p.out_dim - n * 128 + 15) & ~15);
+          const uint32_t idesc = (1u << 4) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);
           for (int kc = 0; kc < kFW / kHK; ++kc, ++qr) {
             if (n == 0 && (kc & 1) == 0) {  // activation columns [128 (kc/2), +128) written and visible to the MMA proxy
               mbar_wait(&act_ready[kc >> 1], ar & 1);
@@ -346,9 +349,9 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
               for (int k = 0; k < kHK / 16; ++k) {
                 const uint64_t koff = (uint64_t)((k * 32) >> 4);
                 const uint32_t first = (kc | k) ? 1u : 0u;
-                tc_mma_f16(d1, ah + koff, bl + koff, kFIdesc, first);
-                tc_mma_f16(d1, al + koff, bh + koff, kFIdesc, 1u);
-                tc_mma_f16(d0, ah + koff, bh + koff, kFIdesc, first);
+                tc_mma_f16(d1, ah + koff, bl + koff, idesc, first);
+                tc_mma_f16(d1, al + koff, bh + koff, idesc, 1u);
+                tc_mma_f16(d0, ah + koff, bh + koff, idesc, first);
               }
               tc_commit(&r_empty[s]);
               if (kc == kFW / kHK - 1) tc_commit(&tfull[b]);

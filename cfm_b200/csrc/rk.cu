@@ -206,7 +206,23 @@ __global__ void rk_init_reduce_a(const cfm_rk_state* __restrict__ st, const floa
   const float atol = st->atol, rtol = st->rtol;
   double a0 = 0.0, a1 = 0.0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
+  const int64_t n4 = ((numel & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(f0)) & 15) == 0)
+                         ? (numel >> 2) : 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {  // 128-bit loads
+    const float4 xv = reinterpret_cast<const float4*>(x)[i], fv = reinterpret_cast<const float4*>(f0)[i];
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, fs[4] = {fv.x, fv.y, fv.z, fv.w};
+    float s0 = 0.f, s1 = 0.f;  // four squares per partial: fp32 is ample, the long sums are float64
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float sc = atol + fabsf(xs[c]) * rtol;
+      const float p = xs[c] / sc, q = fs[c] / sc;
+      s0 = fmaf(p, p, s0);
+      s1 = fmaf(q, q, s1);
+    }
+    a0 += (double)s0;
+    a1 += (double)s1;
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
     const float sc = atol + fabsf(x[i]) * rtol;
     const float p = x[i] / sc, q = f0[i] / sc;
     a0 += (double)p * p;

@@ -765,7 +765,9 @@ int sinkhorn_v2_launch(SkParams& p, cudaStream_t s) {
   if (pf < 0) { const char* e = getenv("CFM_SK_PF"); pf = e ? atoi(e) : 0; }
   p.prefetch_chunks = ((size_t)p.n0 * p.n1 * 4 > (size_t)100 << 20) ? pf : 0;  // pointless when M lives in L2 anyway
   static int atom = -1;  // CFM_SK_ATOMIC: 1 = single-barrier iteration (fixed-point atomic column sums), 0 = two barriers + combine
-  if (atom < 0) { const char* e = getenv("CFM_SK_ATOMIC"); atom = e ? atoi(e) : 1; }
+  // measured at C2 on one box: two barriers + sliced combine 4.435 ms, single barrier + 1.2 M 64-bit L2 atomics per
+  // iteration 5.62 ms -- the atomics cost three times what the second barrier and the combine do; default off
+  if (atom < 0) { const char* e = getenv("CFM_SK_ATOMIC"); atom = e ? atoi(e) : 0; }
   p.atomic_cols = atom;
   static long persist = -2;  // CFM_SK_PERSIST_MB: raise cudaLimitPersistingL2CacheSize before the first solve (experiment)
   if (persist == -2) {
