@@ -120,7 +120,7 @@ extern "C" int cfm_mlp_forward_f32(const void* prepared, const float* x, int bat
   const char* B = reinterpret_cast<const char*>(prepared);
   if (use_tc)
     return mlp_tc_forward(h, prepared, x, nullptr, nullptr, batch, t_dev, t_host, act, y, workspace,
-                          workspace_bytes, s);
+                          workspace_bytes, nullptr, s);
   auto P = [&](int64_t off) { return reinterpret_cast<const float*>(B + off); };
   float* hA = reinterpret_cast<float*>(workspace);
   float* hB = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align_up((size_t)batch * w * 4, 256));
@@ -143,11 +143,19 @@ extern "C" int cfm_mlp_forward_split_f32(const void* prepared, const void* x_hi,
                                          int dim, int w, int out_dim, int time_varying, const float* t_dev,
                                          float t_host, int act, float* y, void* workspace,
                                          size_t workspace_bytes, void* stream) {
+  return cfm_mlp_forward_split_gated_f32(prepared, x_hi, x_lo, batch, dim, w, out_dim, time_varying, t_dev, t_host,
+                                         act, y, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int cfm_mlp_forward_split_gated_f32(const void* prepared, const void* x_hi, const void* x_lo, int batch,
+                                               int dim, int w, int out_dim, int time_varying, const float* t_dev,
+                                               float t_host, int act, float* y, const int32_t* skip_if_nonzero,
+                                               void* workspace, size_t workspace_bytes, void* stream) {
   CFM_REQUIRE(prepared && x_hi && x_lo && y && workspace, "cfm_mlp_forward_split_f32: null pointer");
   CFM_REQUIRE(act == CFM_ACT_SELU || act == CFM_ACT_SILU, "cfm_mlp_forward_split_f32: unknown activation %d", act);
   CFM_REQUIRE(mlp_tc_supported(batch, dim, w, out_dim) != 0,
               "cfm_mlp_forward_split_f32: shape not supported by the tensor-core path");
   const MlpBlobHeader h = mlp_layout(dim, w, out_dim, time_varying ? 1 : 0);
   return mlp_tc_forward(h, prepared, nullptr, x_hi, x_lo, batch, t_dev, t_host, act, y, workspace,
-                        workspace_bytes, (cudaStream_t)stream);
+                        workspace_bytes, skip_if_nonzero, (cudaStream_t)stream);
 }

@@ -16,7 +16,7 @@ int mlp_tc_supported(int batch, int dim, int w, int out_dim);
 size_t mlp_tc_workspace_bytes(int batch, int dim, int w, int out_dim);
 int mlp_tc_forward(const MlpBlobHeader& h, const void* blob, const float* x, const void* x_hi,
                    const void* x_lo, int batch, const float* t_dev, float t_host, int act, float* y, void* ws,
-                   size_t ws_bytes, cudaStream_t s);
+                   size_t ws_bytes, const int32_t* skip, cudaStream_t s);
 
 static inline MlpBlobHeader mlp_layout(int dim, int w, int out_dim, int tv) {
   MlpBlobHeader h;

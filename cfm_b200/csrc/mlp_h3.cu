@@ -183,6 +183,7 @@ struct FusedParams {
   const float* t_dev;   // device scalar or null
   float t_host;
   float* y;             // (batch, out_dim) fp32
+  const int32_t* skip;  // nullable device flag: non-zero = return at once (a step enqueued after the integration finished)
   unsigned long long* dbg;  // optional per-CTA globaltimer checkpoints (64 per CTA), see scripts/mlp_timeline.py
 };
 #define F_MARK(slot) do { if (p.dbg) p.dbg[blockIdx.x * 64 + (slot)] = tc_now(); } while (0)
@@ -214,6 +215,7 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.skip != nullptr && __ldg(p.skip) != 0) return;  // uniform over the grid; nothing has been allocated yet
   if (threadIdx.x == 0) F_MARK(0);
   const int num_slabs = (p.batch + kTM - 1) / kTM;
   const int nk1 = (p.dim + kHK - 1) / kHK;
@@ -517,7 +519,7 @@ static int fused_mode() {  // CFM_MLP_FUSED=0 forces the per-layer launches (A/B
 
 int mlp_tc_forward(const MlpBlobHeader& h, const void* blob, const float* x, const void* x_hi_v,
                    const void* x_lo_v, int batch, const float* t_dev, float t_host, int act, float* y, void* ws,
-                   size_t ws_bytes, cudaStream_t s) {
+                   size_t ws_bytes, const int32_t* skip, cudaStream_t s) {
   const H3MlpWs W = h3_mlp_ws(batch, h.dim, h.w);
   CFM_REQUIRE(ws_bytes >= W.total, "mlp tcgen05: workspace too small (%zu < %zu)", ws_bytes, W.total);
   CFM_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x_hi_v) | reinterpret_cast<uintptr_t>(x_lo_v) |
@@ -555,7 +557,7 @@ int mlp_tc_forward(const MlpBlobHeader& h, const void* blob, const float* x, con
     FusedParams p;
     p.batch = batch; p.dim = h.dim; p.out_dim = h.out_dim; p.act = act;
     for (int l = 0; l < 4; ++l) { p.bias[l] = F(boff[l]); p.inv_ws[l] = IS(l); }
-    p.tcol = tcol; p.t_dev = t_dev; p.t_host = t_host; p.y = y;
+    p.tcol = tcol; p.t_dev = t_dev; p.t_host = t_host; p.y = y; p.skip = skip;
     p.dbg = tc_debug_buffer();
     CFM_CUDA_OK(cudaFuncSetAttribute(mlp_fused_h3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFSmemBytes));
     int grid = (batch + kTM - 1) / kTM;

@@ -65,7 +65,8 @@ __device__ __forceinline__ double block_sum_to(double v, double* smem32) {
 __global__ void rk_stage_input_kernel(const cfm_rk_state* __restrict__ st, const float* __restrict__ x,
                                       const float* __restrict__ k, float* __restrict__ out,
                                       __half* __restrict__ out_hi, __half* __restrict__ out_lo,
-                                      float* __restrict__ t_stage, int64_t numel, int stage) {
+                                      float* __restrict__ t_stage, float* __restrict__ err_partial, int64_t numel,
+                                      int stage) {
   if (st->done) return;
   const float dt = st->dt;
   if (blockIdx.x == 0 && threadIdx.x == 0 && t_stage) *t_stage = st->t + kC[stage] * dt;
@@ -76,14 +77,20 @@ __global__ void rk_stage_input_kernel(const cfm_rk_state* __restrict__ st, const
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 v = reinterpret_cast<const float4*>(x)[i];
+    float4 e6 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
       if (j < stage && kA[stage][j] != 0.f) {
         const float4 kk = reinterpret_cast<const float4*>(k + (int64_t)j * numel)[i];
         v.x = fmaf(a[j], kk.x, v.x); v.y = fmaf(a[j], kk.y, v.y);
         v.z = fmaf(a[j], kk.z, v.z); v.w = fmaf(a[j], kk.w, v.w);
+        if (err_partial) {  // stage 6 reads k1..k6 anyway: hand the error estimate's first six terms to the norm kernel
+          e6.x = fmaf(kE[j], kk.x, e6.x); e6.y = fmaf(kE[j], kk.y, e6.y);
+          e6.z = fmaf(kE[j], kk.z, e6.z); e6.w = fmaf(kE[j], kk.w, e6.w);
+        }
       }
     }
+    if (err_partial) reinterpret_cast<float4*>(err_partial)[i] = e6;
     if (out) reinterpret_cast<float4*>(out)[i] = v;
     if (out_hi) {  // operand pair for the tensor-core MLP: the fp32 stage input is never re-read
       __half h[4], l[4];
@@ -98,8 +105,12 @@ __global__ void rk_stage_input_kernel(const cfm_rk_state* __restrict__ st, const
     }
   }
   for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
-    float v = x[i];
-    for (int j = 0; j < stage; ++j) v = fmaf(a[j], k[(int64_t)j * numel + i], v);
+    float v = x[i], e6 = 0.f;
+    for (int j = 0; j < stage; ++j) {
+      v = fmaf(a[j], k[(int64_t)j * numel + i], v);
+      if (kA[stage][j] != 0.f) e6 = fmaf(kE[j], k[(int64_t)j * numel + i], e6);
+    }
+    if (err_partial) err_partial[i] = e6;
     if (out) out[i] = v;
     if (out_hi) { __half h, l; rk_split_h3(v, h, l); out_hi[i] = h; out_lo[i] = l; }
   }
@@ -108,7 +119,7 @@ __global__ void rk_stage_input_kernel(const cfm_rk_state* __restrict__ st, const
 // err_acc += sum( (dt * sum_j e_j k_j / (atol + rtol * max(|x|, |xnew|)))^2 )
 __global__ void rk_error_norm_kernel(cfm_rk_state* st, const float* __restrict__ x,
                                      const float* __restrict__ xnew, const float* __restrict__ k,
-                                     int64_t numel) {
+                                     const float* __restrict__ err_partial, int64_t numel) {
   __shared__ double red[32];
   if (st->done) return;
   const float dt = st->dt, atol = st->atol, rtol = st->rtol;
@@ -116,9 +127,13 @@ __global__ void rk_error_norm_kernel(cfm_rk_state* st, const float* __restrict__
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
     float e = 0.f;
+    if (err_partial) {  // sum_{j<=6} e_j k_j was accumulated by the stage-6 kernel (same order of operations)
+      e = fmaf(kE[6], k[6 * numel + i], err_partial[i]);
+    } else {
 #pragma unroll
-    for (int j = 0; j < 7; ++j)
-      if (kE[j] != 0.f) e = fmaf(kE[j], k[(int64_t)j * numel + i], e);
+      for (int j = 0; j < 7; ++j)
+        if (kE[j] != 0.f) e = fmaf(kE[j], k[(int64_t)j * numel + i], e);
+    }
     e *= dt;
     const float tol = atol + rtol * fmaxf(fabsf(x[i]), fabsf(xnew[i]));
     const float r = e / tol;
@@ -296,21 +311,23 @@ using namespace cfm;
 #define RK_CHECK(cond) CFM_REQUIRE(cond, "%s: bad argument (" #cond ")", __func__)
 
 extern "C" int cfm_rk_stage_input(const cfm_rk_state* st, const float* x, const float* k, float* out,
-                                  void* out_hi, void* out_lo, float* t_stage, int64_t numel, int stage,
-                                  void* stream) {
+                                  void* out_hi, void* out_lo, float* t_stage, float* err_partial, int64_t numel,
+                                  int stage, void* stream) {
   RK_CHECK(st && x && k && (out || out_hi) && numel > 0 && stage >= 1 && stage <= 6);
   RK_CHECK((out_hi == nullptr) == (out_lo == nullptr));
   RK_CHECK(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(out) |
              reinterpret_cast<uintptr_t>(out_hi) | reinterpret_cast<uintptr_t>(out_lo)) & 15) == 0);
+  RK_CHECK(err_partial == nullptr || stage == 6);
   rk_stage_input_kernel<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(
-      st, x, k, out, reinterpret_cast<__half*>(out_hi), reinterpret_cast<__half*>(out_lo), t_stage, numel, stage); ::cfm::note_launches(1);
+      st, x, k, out, reinterpret_cast<__half*>(out_hi), reinterpret_cast<__half*>(out_lo), t_stage, err_partial, numel,
+      stage); ::cfm::note_launches(1);
   CFM_CUDA_OK(cudaGetLastError());
   return CFM_OK;
 }
 extern "C" int cfm_rk_error_norm(cfm_rk_state* st, const float* x, const float* xnew, const float* k,
-                                 int64_t numel, void* stream) {
+                                 const float* err_partial, int64_t numel, void* stream) {
   RK_CHECK(st && x && xnew && k && numel > 0);
-  rk_error_norm_kernel<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(st, x, xnew, k, numel); ::cfm::note_launches(1);
+  rk_error_norm_kernel<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(st, x, xnew, k, err_partial, numel); ::cfm::note_launches(1);
   CFM_CUDA_OK(cudaGetLastError());
   return CFM_OK;
 }

@@ -117,18 +117,20 @@ class MLP(torch.nn.Module):
             return False
         return bool(_ffi.lib().cfm_mlp_tc_supported(batch, self.net[0].in_features - 1, self.w, self.out_dim))
 
-    def vector_field_split(self, t_dev, x_hi, x_lo, out):
-        """vector_field for an input already stored as its TF32 operand pair (x = x_hi + x_lo), as the
-        dopri5 stage-input kernel writes it; ``t_dev`` is a 1-element CUDA tensor."""
+    def vector_field_split(self, t_dev, x_hi, x_lo, out, skip_flag=None):
+        """vector_field for an input already stored as its fp16x3 tensor-core operand pair (x_hi, x_lo fp16), as
+        the dopri5 stage-input kernel writes it; ``t_dev`` is a 1-element CUDA tensor.  ``skip_flag``: optional
+        1-element int32 CUDA tensor; the fused kernel returns at once when it is non-zero."""
         L = _ffi.lib()
         dev = x_hi.device
         dim = self.net[0].in_features - 1
         B = x_hi.shape[0]
         blob = self._prepared(True, dev)
         ws = _ffi.workspace(L.cfm_mlp_workspace_bytes(B, dim, self.w, self.out_dim, 2), dev)
-        _ffi.check(L.cfm_mlp_forward_split_f32(
+        _ffi.check(L.cfm_mlp_forward_split_gated_f32(
             _ffi.ptr(blob), _ffi.ptr(x_hi), _ffi.ptr(x_lo), B, dim, self.w, self.out_dim, 1, _ffi.ptr(t_dev), 0.0,
-            self.act, _ffi.ptr(out), _ffi.ptr(ws), ws.numel(), _ffi.stream_ptr(dev)), "cfm_mlp_forward_split_f32")
+            self.act, _ffi.ptr(out), _ffi.ptr(skip_flag), _ffi.ptr(ws), ws.numel(), _ffi.stream_ptr(dev)),
+            "cfm_mlp_forward_split_gated_f32")
         return out
 
 

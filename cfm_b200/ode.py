@@ -48,6 +48,9 @@ class NeuralODE(torch.nn.Module):
         self.stats = {}
         self.use_cuda_graph = True  # replay one captured dopri5 step per iteration
         self.max_burst = 32         # steps enqueued between two host reads of the controller state
+        self.min_burst = 4          # ... at least this many: a step enqueued after the end is 15 empty launches (every
+                                    # kernel, the fused MLP included, checks the device-side `done` flag), cheaper
+                                    # than a host round trip per step
         self.use_fused_small = True  # small MLPs: the whole trajectory in one launch (csrc/ode_small.cu)
         # Row-sharded integration across ranks (cfm_b200.dist.sharded_trajectory(..., lockstep=True)): a
         # torch.distributed group (or True for the default group).  torchdyn's controller uses ONE error norm
@@ -139,14 +142,15 @@ class NeuralODE(torch.nn.Module):
                 # (= xnew, needed by the error norm and the commit) is also kept in fp32
                 _ffi.check(L.cfm_rk_stage_input(stp, _ffi.ptr(x), _ffi.ptr(k), _ffi.ptr(out if stage == 6 else None),
                                                 _ffi.ptr(P["xs_hi"]), _ffi.ptr(P["xs_lo"]), _ffi.ptr(P["t_stage"]),
+                                                _ffi.ptr(xs if stage == 6 else None),  # error partial -> xs (free here)
                                                 numel, stage, sp), "cfm_rk_stage_input")
-                mlp.vector_field_split(P["t_stage"], P["xs_hi"], P["xs_lo"], k[stage])
+                mlp.vector_field_split(P["t_stage"], P["xs_hi"], P["xs_lo"], k[stage], skip_flag=P["done_flag"])
             else:
                 _ffi.check(L.cfm_rk_stage_input(stp, _ffi.ptr(x), _ffi.ptr(k), _ffi.ptr(out), None, None,
-                                                _ffi.ptr(P["t_stage"]), numel, stage, sp), "cfm_rk_stage_input")
+                                                _ffi.ptr(P["t_stage"]), None, numel, stage, sp), "cfm_rk_stage_input")
                 mlp.vector_field(P["t_stage"], out, out=k[stage])
-        _ffi.check(L.cfm_rk_error_norm(stp, _ffi.ptr(x), _ffi.ptr(xnew), _ffi.ptr(k), numel, sp),
-                   "cfm_rk_error_norm")
+        _ffi.check(L.cfm_rk_error_norm(stp, _ffi.ptr(x), _ffi.ptr(xnew), _ffi.ptr(k),
+                                       _ffi.ptr(xs if split else None), numel, sp), "cfm_rk_error_norm")
         if P["group"] is not None:  # lock-step: the error norm is over the rows of ALL ranks
             P["dist"].all_reduce(P["err_acc"], group=P["group"])
         _ffi.check(L.cfm_rk_control(stp, _ffi.ptr(P["t_span"]), P["numel_global"], sp), "cfm_rk_control")
@@ -174,6 +178,8 @@ class NeuralODE(torch.nn.Module):
              "xs_hi": None, "xs_lo": None, "graph": None, "group": None, "dist": None, "numel_global": B * D}
         off = _ffi.RkState.err_acc.offset  # the float64 accumulator inside the device state struct
         P["err_acc"] = st[off:off + 8].view(torch.float64)
+        off = _ffi.RkState.done.offset  # int32: non-zero once t has reached t_end
+        P["done_flag"] = st[off:off + 4].view(torch.int32)
         if mlp.tc_path(B):
             # stage inputs go to the MLP as its fp16x3 tensor-core operand pair (hi, lo), written by the RK kernel
             P["xs_hi"] = torch.empty((B, D), dtype=torch.float16, device=dev)
@@ -251,7 +257,7 @@ class NeuralODE(torch.nn.Module):
             # be recorded costs at least one accepted step (the controller clips dt onto it), so that
             # many steps can be enqueued without looking; a step enqueued after t_end is a no-op on the
             # device (done flag), so the bound only has to be safe, not tight.
-            burst = max(1, min(self.max_burst, n_span - int(cur.ckpt)))
+            burst = max(1 if lock else self.min_burst, min(self.max_burst, n_span - int(cur.ckpt)))
             for _ in range(burst):
                 if P["graph"] is not None and not lock:
                     P["graph"].replay()

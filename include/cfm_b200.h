@@ -220,6 +220,13 @@ int cfm_mlp_forward_split_f32(const void* prepared, const void* x_hi, const void
                               int dim, int w, int out_dim, int time_varying, const float* t_dev,
                               float t_host, int act, float* y, void* workspace,
                               size_t workspace_bytes, void* stream);
+/* The same with a device-side gate: when *skip_if_nonzero != 0 (nullable) the fused kernel returns at once.  The
+ * dopri5 driver passes &state->done, so that steps enqueued speculatively after the integration has finished cost a
+ * launch, not a forward (the per-layer path ignores the gate: its result is simply unused). */
+int cfm_mlp_forward_split_gated_f32(const void* prepared, const void* x_hi, const void* x_lo, int batch,
+                                    int dim, int w, int out_dim, int time_varying, const float* t_dev,
+                                    float t_host, int act, float* y, const int32_t* skip_if_nonzero,
+                                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- (a11) dopri5 lock-step driver pieces -------------------------------------------
  * replaces the arithmetic of torchdyn's NeuralODE(solver="dopri5").trajectory (call
@@ -248,13 +255,16 @@ typedef struct cfm_rk_state {
  * stage 6: the same with the 5th-order weights, i.e. out = xnew (and the FSAL input).
  * out (nullable) receives the fp32 value; out_hi/out_lo (nullable pair, fp16 arrays of numel elements)
  * receive its fp16x3 operand split, the form cfm_mlp_forward_split_f32 consumes.  *t_stage (device
- * float, nullable) = t + c[stage]*dt. */
+ * float, nullable) = t + c[stage]*dt.  err_partial (nullable, stage 6 only, numel floats): receives
+ * sum_{j<=6} e_j k_j, the first six terms of the embedded error estimate -- stage 6 reads k1..k6 anyway, so
+ * cfm_rk_error_norm can then read four arrays instead of eight. */
 int cfm_rk_stage_input(const cfm_rk_state* st, const float* x, const float* k, float* out,
-                       void* out_hi, void* out_lo, float* t_stage, int64_t numel, int stage,
-                       void* stream);
-/* st->err_acc += sum((dt*sum_j e_j k_j / (atol + rtol*max(|x|,|xnew|)))^2) */
+                       void* out_hi, void* out_lo, float* t_stage, float* err_partial, int64_t numel,
+                       int stage, void* stream);
+/* st->err_acc += sum((dt*sum_j e_j k_j / (atol + rtol*max(|x|,|xnew|)))^2); with err_partial (see above) the
+ * sum over j is err_partial + e_7 k_7 */
 int cfm_rk_error_norm(cfm_rk_state* st, const float* x, const float* xnew, const float* k,
-                      int64_t numel, void* stream);
+                      const float* err_partial, int64_t numel, void* stream);
 /* accept/reject, checkpoint bookkeeping, step-size adaptation, clipping of the next dt */
 int cfm_rk_control(cfm_rk_state* st, const float* t_span, int64_t numel, void* stream);
 /* if the step was accepted: x <- xnew, k1 <- k7 (FSAL), traj[save_slot] <- xnew */
