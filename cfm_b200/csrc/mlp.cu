@@ -24,6 +24,9 @@ __global__ void mlp_split_w0_kernel(const float* __restrict__ W0, int w, int dim
   if (threadIdx.x == 0) w0t[n] = in0 > dim ? W0[(int64_t)n * in0 + dim] : 0.f;
 }
 
+// the blob header travels as a kernel argument (by value): no host buffer has to outlive the call, no sync
+__global__ void mlp_write_header_kernel(const MlpBlobHeader h, MlpBlobHeader* dst) { *dst = h; }
+
 struct BiasActEpilogue {
   const float* bias;   // (N)
   const float* tcol;   // (N) or null: + t * tcol[n]
@@ -73,7 +76,7 @@ extern "C" int cfm_mlp_prepare(const float* W0, const float* b0, const float* W1
   CFM_REQUIRE(prepared_bytes >= (size_t)h.total, "cfm_mlp_prepare: blob too small (%zu < %lld)",
               prepared_bytes, (long long)h.total);
   char* B = reinterpret_cast<char*>(prepared);
-  CFM_CUDA_OK(cudaMemcpyAsync(B, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+  mlp_write_header_kernel<<<1, 1, 0, s>>>(h, reinterpret_cast<MlpBlobHeader*>(B)); ::cfm::note_launches(1);
   const int in0 = dim + (time_varying ? 1 : 0);
   mlp_split_w0_kernel<<<w, 256, 0, s>>>(W0, w, dim, in0, h.dimp, reinterpret_cast<float*>(B + h.off_w0x),
                                         reinterpret_cast<float*>(B + h.off_w0t)); ::cfm::note_launches(1);
@@ -88,8 +91,6 @@ extern "C" int cfm_mlp_prepare(const float* W0, const float* b0, const float* W1
   CFM_CUDA_OK(cp(h.off_b2, b2, w));
   CFM_CUDA_OK(cp(h.off_w3, W3, (size_t)out_dim * w));
   CFM_CUDA_OK(cp(h.off_b3, b3, out_dim));
-  // the header copy above reads a stack object: make sure it has been consumed before returning
-  CFM_CUDA_OK(cudaStreamSynchronize(s));
   return mlp_tc_prepare(h, prepared, s);
 }
 

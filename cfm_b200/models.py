@@ -61,9 +61,10 @@ class MLP(torch.nn.Module):
                 if p.device != device or p.dtype != torch.float32:
                     raise _ffi.CfmLibraryError("MLP parameters must be fp32 on the input's CUDA device")
                 ps.append(p.detach().contiguous())
-        _ffi.check(L.cfm_mlp_prepare(*[_ffi.ptr(p) for p in ps], dim, self.w, self.out_dim, tv,
-                                     _ffi.ptr(blob), nbytes, _ffi.stream_ptr(device)),
-                   "cfm_mlp_prepare")
+        with torch.cuda.device(device):
+            _ffi.check(L.cfm_mlp_prepare(*[_ffi.ptr(p) for p in ps], dim, self.w, self.out_dim, tv,
+                                         _ffi.ptr(blob), nbytes, _ffi.stream_ptr(device)),
+                       "cfm_mlp_prepare")
         self._blobs[key] = (ver, blob)
         return blob
 
@@ -79,10 +80,11 @@ class MLP(torch.nn.Module):
         blob = self._prepared(split_t, dev)
         y = out if out is not None else torch.empty((B, self.out_dim), dtype=torch.float32, device=dev)
         ws = _ffi.workspace(L.cfm_mlp_workspace_bytes(B, dim, self.w, self.out_dim, self.mlp_algo), dev)
-        _ffi.check(L.cfm_mlp_forward_f32(
-            _ffi.ptr(blob), _ffi.ptr(x), B, dim, self.w, self.out_dim, 1 if split_t else 0,
-            _ffi.ptr(t_dev), float(t_host), self.act, _ffi.ptr(y), self.mlp_algo, _ffi.ptr(ws),
-            ws.numel(), _ffi.stream_ptr(dev)), "cfm_mlp_forward_f32")
+        with torch.cuda.device(dev):  # kernels launch on the current device: make it the tensors' one
+            _ffi.check(L.cfm_mlp_forward_f32(
+                _ffi.ptr(blob), _ffi.ptr(x), B, dim, self.w, self.out_dim, 1 if split_t else 0,
+                _ffi.ptr(t_dev), float(t_host), self.act, _ffi.ptr(y), self.mlp_algo, _ffi.ptr(ws),
+                ws.numel(), _ffi.stream_ptr(dev)), "cfm_mlp_forward_f32")
         return y
 
     def _use_kernels(self, x):

@@ -71,6 +71,10 @@ class NeuralODE(torch.nn.Module):
         if not x.is_cuda:
             raise _ffi.CfmLibraryError("NeuralODE.trajectory needs CUDA inputs (no CPU fallback)")
         dev = x.device
+        with torch.cuda.device(dev):  # the library launches on the CURRENT device: make it the tensors' one
+            return self._trajectory_on(mlp, x, t_span, dev)
+
+    def _trajectory_on(self, mlp, x, t_span, dev):
         shape = x.shape
         x0 = x.detach().reshape(shape[0], -1).float().contiguous()
         t_span = torch.as_tensor(t_span, dtype=torch.float32)
