@@ -16,7 +16,9 @@
 //            epilogue functor:  begin_row(row, ok); store32(row0, lane, col0, acc[32], n_rows, n_cols, tile)
 //            -- called by the whole warp, which writes the chunk coalesced via tc_store_chunk32; finish(lane).
 // Tile = 128 x 256 outputs; tiles are walked M-fastest so the B panel stays hot in L2.
-// Users: sqdist_tc.cu (cost matrix), mlp_tc.cu (vector-field MLP layers).
+// Users: sqdist_tc.cu (cost matrix, algo 2: round 1's path, kept for A/B).  The PTX wrappers below (mbarrier, TMA,
+// tcgen05 fences / commit / ld, the SW128 descriptor, the coalesced chunk store) are shared with gemm_h3.cuh, the
+// fp16x3 core that serves the cost matrix and the MLP by default.
 #pragma once
 #include <cuda.h>
 #include <stdlib.h>

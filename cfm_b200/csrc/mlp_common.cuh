@@ -1,4 +1,4 @@
-// Shared between mlp.cu (SIMT path, prepare/forward entry points) and mlp_tc.cu (tcgen05 path).
+// Shared between mlp.cu (SIMT path, prepare/forward entry points) and mlp_h3.cu (tcgen05 paths).
 #pragma once
 #include "common.cuh"
 

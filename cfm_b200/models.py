@@ -30,7 +30,7 @@ class MLP(torch.nn.Module):
             torch.nn.Linear(w, out_dim),
         )
         self.act = _ffi.ACT_SELU
-        self.mlp_algo = 0  # 0 auto, 1 SIMT fp32, 2 tcgen05 3xTF32
+        self.mlp_algo = 0  # 0 auto, 1 SIMT fp32, 2 tcgen05 (fp16x3 scheme: fused kernel for w = 256, per-layer otherwise)
         self._blobs = {}   # (split_t, device) -> (version key, prepared blob tensor)
 
     # -- prepared weights (rebuilt when any parameter changes in place or is replaced) ------

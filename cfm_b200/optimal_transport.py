@@ -99,7 +99,8 @@ class OTPlanSampler:
     precision : 'auto' | 'fp32' | 'fp64' | 'fp64-mixed' exponent arithmetic of the Sinkhorn kernel
         ('fp64-mixed': float64 potentials and exponent arguments, fp32 exponentials).
     stall_tol : stop once an fp32 fixed point is reached (see include/cfm_b200.h); 0 disables.
-    cost_algo : 0 auto, 1 SIMT fp32, 2 tcgen05 3xTF32.
+    cost_algo : 0 auto (fp16x3 tensor-core path for aligned shapes; SIMT for exact OT), 1 SIMT fp32,
+        2 tcgen05 3xTF32 (round-1 path, kept for A/B), 3 tcgen05 fp16x3.
     """
 
     def __init__(
