@@ -261,6 +261,16 @@ typedef struct cfm_rk_state {
 int cfm_rk_stage_input(const cfm_rk_state* st, const float* x, const float* k, float* out,
                        void* out_hi, void* out_lo, float* t_stage, float* err_partial, int64_t numel,
                        int stage, void* stream);
+/* The stage input in two pieces, so that the bulk of it overlaps the vector-field evaluation that precedes it
+ * (stage in 2..6, numel % 4 == 0):  cfm_rk_stage_partial writes  partial = x + dt*sum_{j<stage-1} a[stage][j]*k_j
+ * -- everything that does not need the newest derivative k_stage -- and *t_stage; it can run on a side stream
+ * while the MLP computes k_stage.  cfm_rk_stage_finish then forms  partial + dt*a[stage][stage-1]*k_stage  and
+ * writes it like cfm_rk_stage_input does.  Same fp32 operations in the same order: bit-identical stage inputs.
+ * err_partial (nullable, stage 6): partial writes sum_{j<5} e_j k_j, finish adds e_6 k_6 in place. */
+int cfm_rk_stage_partial(const cfm_rk_state* st, const float* x, const float* k, float* partial,
+                         float* err_partial, float* t_stage, int64_t numel, int stage, void* stream);
+int cfm_rk_stage_finish(const cfm_rk_state* st, const float* partial, const float* k, float* out, void* out_hi,
+                        void* out_lo, float* err_partial, int64_t numel, int stage, void* stream);
 /* st->err_acc += sum((dt*sum_j e_j k_j / (atol + rtol*max(|x|,|xnew|)))^2); with err_partial (see above) the
  * sum over j is err_partial + e_7 k_7 */
 int cfm_rk_error_norm(cfm_rk_state* st, const float* x, const float* xnew, const float* k,
