@@ -330,3 +330,60 @@ def test_dopri5_config3_full_batch_one_launch_per_nfe():
     # The four-launches-per-forward design needs 33 per step.
     steps = node.stats["accepted"] + node.stats["rejected"]
     assert launches <= 8 + (steps + 1) * 15, (launches, steps)
+
+
+# ------------------------------------------------------------------------- dopri5 driver, split stage inputs
+def _rk_state(dt=0.0625, t=0.25):
+    st = _ffi.RkState()
+    st.t, st.dt, st.t_end, st.atol, st.rtol = t, dt, 1.0, 1e-4, 1e-4
+    st.n_span, st.ckpt, st.save_slot = 2, 1, -1
+    return torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8).to(DEV)
+
+
+@pytest.mark.parametrize("stage", [2, 3, 4, 5, 6])
+def test_rk_stage_partial_plus_finish_is_bit_identical_to_the_one_piece_kernel(stage):
+    """cfm_rk_stage_partial (everything but the newest derivative; runs on a side stream during the MLP) followed by
+    cfm_rk_stage_finish performs the same fp32 operations in the same order as cfm_rk_stage_input."""
+    L = _ffi.lib()
+    B, D = 513, 64
+    numel = B * D
+    g = torch.Generator().manual_seed(stage)
+    x = torch.randn(B, D, generator=g).to(DEV)
+    k = torch.randn(7, B, D, generator=g).to(DEV)
+    st = _rk_state()
+    sp = _ffi.stream_ptr(torch.device(DEV))
+    f32 = lambda: torch.zeros(B, D, dtype=torch.float32, device=DEV)  # noqa: E731
+    f16 = lambda: torch.zeros(B, D, dtype=torch.float16, device=DEV)  # noqa: E731
+    out_a, hi_a, lo_a, e_a, t_a = f32(), f16(), f16(), f32(), torch.zeros(1, device=DEV)
+    _ffi.check(L.cfm_rk_stage_input(_ffi.ptr(st), _ffi.ptr(x), _ffi.ptr(k), _ffi.ptr(out_a), _ffi.ptr(hi_a), _ffi.ptr(lo_a),
+                                    _ffi.ptr(t_a), _ffi.ptr(e_a) if stage == 6 else None, numel, stage, sp), "stage_input")
+    part, out_b, hi_b, lo_b, e_b, t_b = f32(), f32(), f16(), f16(), f32(), torch.zeros(1, device=DEV)
+    _ffi.check(L.cfm_rk_stage_partial(_ffi.ptr(st), _ffi.ptr(x), _ffi.ptr(k), _ffi.ptr(part),
+                                      _ffi.ptr(e_b) if stage == 6 else None, _ffi.ptr(t_b), numel, stage, sp), "partial")
+    _ffi.check(L.cfm_rk_stage_finish(_ffi.ptr(st), _ffi.ptr(part), _ffi.ptr(k), _ffi.ptr(out_b), _ffi.ptr(hi_b), _ffi.ptr(lo_b),
+                                     _ffi.ptr(e_b) if stage == 6 else None, numel, stage, sp), "finish")
+    assert torch.equal(out_a, out_b) and torch.equal(t_a, t_b)
+    assert torch.equal(hi_a.view(torch.int16), hi_b.view(torch.int16)) and torch.equal(lo_a.view(torch.int16), lo_b.view(torch.int16))
+    if stage == 6:
+        assert torch.equal(e_a, e_b)
+    # and the operand pair is the fp16x3 split of the fp32 stage input
+    rec = hi_b.float() + lo_b.float() / 2048.0
+    assert (rec - out_b).abs().max().item() <= 2.0 ** -21 * out_b.abs().max().item()
+
+
+def test_dopri5_overlapped_stage_inputs_equal_the_serial_driver():
+    """Trajectories with the stage inputs split across two streams (graph and eager) are bit-identical to the serial
+    one-stream driver: same kernels' arithmetic, only the schedule differs."""
+    torch.manual_seed(0)
+    m = cfm_b200.MLP(dim=64, w=256, time_varying=True).to(DEV)
+    x = torch.randn(1500, 64, generator=torch.Generator().manual_seed(1)).to(DEV)
+    span = torch.linspace(0, 1, 4)
+    outs = []
+    for overlap, graph in ((False, True), (True, True), (True, False)):
+        node = cfm_b200.NeuralODE(cfm_b200.torch_wrapper(m), solver="dopri5", atol=1e-5, rtol=1e-5)
+        node.overlap_stages, node.use_cuda_graph = overlap, graph
+        node.trajectory(x, span)
+        outs.append((node.trajectory(x, span).clone(), dict(node.stats)))
+    for o, s in outs[1:]:
+        assert torch.equal(o, outs[0][0])
+        assert (s["nfe"], s["accepted"], s["rejected"]) == (outs[0][1]["nfe"], outs[0][1]["accepted"], outs[0][1]["rejected"])
