@@ -58,7 +58,11 @@ class NeuralODE(torch.nn.Module):
         # per step attempt, three more for the initial step) are all-reduced so that every rank takes exactly
         # the step sequence a single process would take on the full batch.
         self.lockstep = None
-        self.overlap_stages = True  # compute the bulk of every stage input on a side stream during the previous MLP
+        # True: compute the bulk of every stage input on a side stream during the previous MLP evaluation
+        # (cfm_rk_stage_partial / _finish).  Bit-identical, but MEASURED SLOWER at C3 (2.38 vs 2.24 ms per trajectory,
+        # same box): the partial kernels compete with the MLP's operand feed for L2 / HBM bandwidth and the finish
+        # kernels add launches -- so the default is the one-piece stage input on one stream.
+        self.overlap_stages = False
         self._plans = {}
 
     @torch.no_grad()
