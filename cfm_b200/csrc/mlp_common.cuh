@@ -54,14 +54,20 @@ __device__ __forceinline__ float act_apply(float x, int act) {
 // error of the result grows, but its ABSOLUTE error stays at ~1.5e-7 (ex2.approx is good to 2^-22 of a value
 // <= 1), which is what the max-norm gate of the MLP (1e-5 of max|y|) sees; the SIMT path keeps expm1f.
 // SiLU through one ex2 and one fast reciprocal.
-__device__ __forceinline__ float act_apply_fast(float x, int act) {
-  if (act == CFM_ACT_SELU) {
+template <int ACT>
+__device__ __forceinline__ float act_fast(float x) {
+  if (ACT == CFM_ACT_SELU) {
     const float scale = 1.0507009873554804934193349852946f;
     const float negcoef = (float)(1.6732632423543772848170429916717 * 1.0507009873554804934193349852946);
-    const float em1 = ex2f(fminf(x, 0.f) * kLog2e) - 1.f;
-    return x > 0.f ? x * scale : em1 * negcoef;
+    // e overflows to +inf for large positive x; the select discards that branch (NaN still propagates: NaN > 0 is false)
+    const float e = ex2f(x * kLog2e);
+    const float neg = fmaf(e, negcoef, -negcoef);
+    return x > 0.f ? x * scale : neg;
   }
   return __fdividef(x, 1.f + ex2f(-x * kLog2e));
+}
+__device__ __forceinline__ float act_apply_fast(float x, int act) {
+  return act == CFM_ACT_SELU ? act_fast<CFM_ACT_SELU>(x) : act_fast<CFM_ACT_SILU>(x);
 }
 
 }  // namespace cfm

@@ -17,18 +17,20 @@
 //     Shared memory: [0,128K) activations (layer 1: ring stage 0), [128K,224K) weight ring (layer 1: stage 1).
 // (2) per-layer launches of the generic fp16x3 GEMM (other widths), hidden activations as fp16 (hi, lo)
 //     pairs in L2.
-// Weights are split once per weight set by cfm_mlp_prepare (row-scaled by powers of two, gemm_h3.cuh).
+// Weights are split once per weight set by cfm_mlp_prepare, scaled by ONE power of two per layer (derived from the
+// layer's max |W|; entries below 4e-9 of it would lose bits, which no trained or initialised layer has), so the
+// epilogues multiply by a kernel-uniform constant; the inv-scale arrays stay per row for the generic core.
 #include "gemm_h3.cuh"
 #include "mlp_common.cuh"
 
 namespace cfm {
 
 int prep_rows_h3(const float* X, int rows, int d, __half* hi, __half* lo, int64_t ldo, float* sqnorm,
-                 float* inv_scale, cudaStream_t s);  // sqdist_h3.cu
+                 float* inv_scale, cudaStream_t s, float* uniform_absmax);  // sqdist_h3.cu
 
 // ---- blob: tensor-core section ------------------------------------------------------------------------
 struct H3Blob {  // byte offsets inside the blob's tensor-core section
-  size_t wh[4], wl[4], is[4], total;
+  size_t wh[4], wl[4], is[4], am, total;
   int64_t ld[4];
 };
 static H3Blob h3_blob(int dimp, int w, int out_dim) {
@@ -42,6 +44,7 @@ static H3Blob h3_blob(int dimp, int w, int out_dim) {
     b.wl[l] = take((size_t)rows[l] * b.ld[l] * 2);
     b.is[l] = take((size_t)rows[l] * 4);
   }
+  b.am = take(4 * sizeof(float));  // per-layer max |W| (sets the layer's power-of-two scale)
   b.total = o;
   return b;
 }
@@ -58,7 +61,8 @@ int mlp_tc_prepare(const MlpBlobHeader& h, void* blob, cudaStream_t s) {
   for (int l = 0; l < 4; ++l) {
     const int rc = prep_rows_h3(reinterpret_cast<const float*>(B + src[l]), rows[l], cols[l],
                                 reinterpret_cast<__half*>(T + tb.wh[l]), reinterpret_cast<__half*>(T + tb.wl[l]),
-                                tb.ld[l], nullptr, reinterpret_cast<float*>(T + tb.is[l]), s);
+                                tb.ld[l], nullptr, reinterpret_cast<float*>(T + tb.is[l]), s,
+                                reinterpret_cast<float*>(T + tb.am) + l);
     if (rc != CFM_OK) return rc;
   }
   return CFM_OK;
@@ -168,11 +172,12 @@ struct MlpH3Epilogue {
 // (1) the fused four-layer kernel (hidden width 256)
 // ======================================================================================================
 constexpr int kFW = 256;                       // hidden width
+constexpr int kFEpiWarpsC = 16;                // epilogue warps (four per TMEM lane quadrant)
 constexpr int kFActBytes = 2 * kTM * kFW * 2;  // 128 KB: hi [4 chunks x 16 KB] | lo [4 chunks x 16 KB]
 constexpr int kFRingStage = 2 * 128 * kHK * 2; // 32 KB: B_hi | B_lo of one 128 x 64 weight tile
 constexpr int kFRingStages = 3;
 constexpr int kFL1Stage = 2 * kHABytes + 2 * kFW * kHK * 2;  // 96 KB: x_hi | x_lo | W0_hi (256 rows) | W0_lo
-constexpr size_t kFSmemBytes = kFActBytes + kFRingStages * kFRingStage + 256;
+constexpr size_t kFSmemBytes = kFActBytes + kFRingStages * kFRingStage + 256 + kFEpiWarpsC * 32 * 4;
 constexpr uint32_t kFIdesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);  // M=128, N=128
 
 struct FusedParams {
@@ -185,14 +190,17 @@ struct FusedParams {
   float* y;             // (batch, out_dim) fp32
   const int32_t* skip;  // nullable device flag: non-zero = return at once (a step enqueued after the integration finished)
   unsigned long long* dbg;  // optional per-CTA globaltimer checkpoints (64 per CTA), see scripts/mlp_timeline.py
+  int probe;  // CFM_MLP_PROBE, timing experiments only (results are WRONG when non-zero): bit0 skip the acc1 read-out,
+              // bit1 skip the epilogue math and stores
 };
 #define F_MARK(slot) do { if (p.dbg) p.dbg[blockIdx.x * 64 + (slot)] = tc_now(); } while (0)
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-constexpr int kFEpiWarps = 16;                   // four per TMEM lane quadrant, one 32-column chunk each
+constexpr int kFEpiWarps = kFEpiWarpsC;          // four per TMEM lane quadrant, one 32-column chunk each
 constexpr int kFThreads = 64 + 32 * kFEpiWarps;  // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 
+template <int ACT>
 __global__ void __launch_bounds__(kFThreads, 1)
 mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                     const __grid_constant__ CUtensorMap map_w0h, const __grid_constant__ CUtensorMap map_w0l,
@@ -213,6 +221,7 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
   uint64_t* act_ready = bars + 14;   // [2] activation columns 0-127 / 128-255 of the current layer are in smem
   uint64_t* slab_done = bars + 16;   // [1] every MMA of the slab has retired
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 17);
+  float* bias_sm = reinterpret_cast<float*>(smem + kFActBytes + kFRingStages * kFRingStage + 256);  // [16 warps][32]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p.skip != nullptr && __ldg(p.skip) != 0) return;  // uniform over the grid; nothing has been allocated yet
@@ -387,17 +396,23 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
         const float* bias = layer == 1 ? p.bias[0] : layer == 2 ? p.bias[1] : layer == 3 ? p.bias[2] : p.bias[3];
         const float* inv_ws = layer == 1 ? p.inv_ws[0] : layer == 2 ? p.inv_ws[1] : layer == 3 ? p.inv_ws[2] : p.inv_ws[3];
         const int col0 = n * 128 + part * 32;  // column of this layer's output
-        // Per-column constants of this warp's 32 columns: lane l fetches column col0 + l (one coalesced 128-byte
-        // load per array) BEFORE waiting for the accumulators, and the unrolled math broadcasts them with
-        // shuffles.  With 224 KB of shared memory in use the L1 is a few KB, so loads issued next to their use
-        // would each pay an L2 round trip on the read-out's critical path.
+        // Per-column bias of this warp's 32 columns: lane l fetches column col0 + l (one coalesced 128-byte load,
+        // issued BEFORE waiting for the accumulators: with 224 KB of shared memory in use the L1 is a few KB and a
+        // load next to its use would pay an L2 round trip on the read-out's critical path) and parks it in the warp's
+        // 128-byte slot of shared memory; the unrolled math reads it back with broadcast 128-bit loads (8 per chunk;
+        // the 64 shuffles per chunk this replaces were a fifth of the read-out: one warp shuffle per clock per SM).
+        // The weight scale is one power of two per layer (cfm_mlp_prepare): a uniform register.
         const int ncols = layer < 4 ? kFW : p.out_dim;
-        float bias_l = 0.f, is_l = 0.f;
+        float bias_l = 0.f;
         if (col0 + lane < ncols) {
           bias_l = __ldg(bias + col0 + lane);
-          is_l = __ldg(inv_ws + col0 + lane);
           if (layer == 1 && p.tcol != nullptr) bias_l = fmaf(t, __ldg(p.tcol + col0 + lane), bias_l);  // + t * W0[:, -1]
         }
+        const float is_u = __ldg(inv_ws);
+        float* bsm = bias_sm + (warp - 2) * 32;
+        __syncwarp();
+        bsm[lane] = bias_l;
+        __syncwarp();
         mbar_wait(&tfull[b], (g >> 1) & 1);
         if (layer < 4 && n == 0) {
           // this layer's other tile still reads the activations this epilogue is about to overwrite
@@ -405,14 +420,24 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
         }
         tc_fence_after();
         if (warp == 2 && lane == 0 && slab == (int)blockIdx.x && tl < 16) F_MARK(8 + 2 * tl);  // accumulators ready
+        // finer marks for tiles 0 (layer 1), 2 (layer 2) and 6 (layer 4): first / last epilogue warp, load vs math
+        const int dbase = (p.dbg != nullptr && lane == 0 && slab == (int)blockIdx.x)
+                              ? (tl == 0 ? 42 : tl == 2 ? 48 : tl == 6 ? 54 : -1) : -1;
+        if (dbase >= 0 && warp == 17) F_MARK(dbase + 1);
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + b * 256u + (uint32_t)(part * 32);
         uint32_t r0[32], r1[32];
         tc_ld32_nowait(taddr, r0);
-        tc_ld32_nowait(taddr + 128, r1);
+        if (!(p.probe & 1)) tc_ld32_nowait(taddr + 128, r1);
+        else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) r1[c] = 0u;
+        }
         tc_ld_wait();
-#define F_BIAS(c) __shfl_sync(0xffffffffu, bias_l, (c))
-#define F_IS(c) __shfl_sync(0xffffffffu, is_l, (c))
-        if (layer < 4) {
+        if (dbase >= 0 && warp == 2) F_MARK(dbase);
+        if (dbase >= 0 && warp == 17) F_MARK(dbase + 2);
+        if (p.probe & 2) {
+          if (r0[0] == 0x7fc12345u) p.y[0] = 0.f;  // keep the loads alive
+        } else if (layer < 4) {
           // activations -> shared memory, K-major 128B-swizzled operand layout:
           // chunk kc = col / 64 (16 KB each), row r at r * 128 B, 16-byte unit u stored at u ^ (r & 7)
           const int kc = col0 >> 6, u0 = (col0 & 63) >> 3;
@@ -424,14 +449,13 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
               const int c = 8 * gq + 4 * q;
-              float a0 = fmaf(__uint_as_float(r1[c]), kH3InvScale, __uint_as_float(r0[c]));
-              float a1 = fmaf(__uint_as_float(r1[c + 1]), kH3InvScale, __uint_as_float(r0[c + 1]));
-              float a2 = fmaf(__uint_as_float(r1[c + 2]), kH3InvScale, __uint_as_float(r0[c + 2]));
-              float a3 = fmaf(__uint_as_float(r1[c + 3]), kH3InvScale, __uint_as_float(r0[c + 3]));
-              a0 = fmaf(a0, F_IS(c), F_BIAS(c)); a1 = fmaf(a1, F_IS(c + 1), F_BIAS(c + 1));
-              a2 = fmaf(a2, F_IS(c + 2), F_BIAS(c + 2)); a3 = fmaf(a3, F_IS(c + 3), F_BIAS(c + 3));
-              v[4 * q] = act_apply_fast(a0, p.act); v[4 * q + 1] = act_apply_fast(a1, p.act);
-              v[4 * q + 2] = act_apply_fast(a2, p.act); v[4 * q + 3] = act_apply_fast(a3, p.act);
+              const float4 b4 = *reinterpret_cast<const float4*>(bsm + c);
+              const float a0 = fmaf(fmaf(__uint_as_float(r1[c]), kH3InvScale, __uint_as_float(r0[c])), is_u, b4.x);
+              const float a1 = fmaf(fmaf(__uint_as_float(r1[c + 1]), kH3InvScale, __uint_as_float(r0[c + 1])), is_u, b4.y);
+              const float a2 = fmaf(fmaf(__uint_as_float(r1[c + 2]), kH3InvScale, __uint_as_float(r0[c + 2])), is_u, b4.z);
+              const float a3 = fmaf(fmaf(__uint_as_float(r1[c + 3]), kH3InvScale, __uint_as_float(r0[c + 3])), is_u, b4.w);
+              v[4 * q] = act_fast<ACT>(a0); v[4 * q + 1] = act_fast<ACT>(a1);
+              v[4 * q + 2] = act_fast<ACT>(a2); v[4 * q + 3] = act_fast<ACT>(a3);
             }
             uint32_t ph[4], pl[4];
 #pragma unroll
@@ -450,11 +474,12 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
             const bool wide = ((reinterpret_cast<uintptr_t>(dst) & 31) == 0);
 #pragma unroll
             for (int c = 0; c < 32; c += 8) {
-              float o[8];
+              float o[8], bq[8];
+              *reinterpret_cast<float4*>(bq) = *reinterpret_cast<const float4*>(bsm + c);
+              *reinterpret_cast<float4*>(bq + 4) = *reinterpret_cast<const float4*>(bsm + c + 4);
 #pragma unroll
               for (int q = 0; q < 8; ++q)
-                o[q] = fmaf(fmaf(__uint_as_float(r1[c + q]), kH3InvScale, __uint_as_float(r0[c + q])), F_IS(c + q),
-                            F_BIAS(c + q));
+                o[q] = fmaf(fmaf(__uint_as_float(r1[c + q]), kH3InvScale, __uint_as_float(r0[c + q])), is_u, bq[q]);
               if (row_ok) {
                 if (wide) {
                   asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + c), "f"(o[0]),
@@ -470,13 +495,11 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
               const float acc = fmaf(__uint_as_float(r1[c]), kH3InvScale, __uint_as_float(r0[c]));
-              const float o = fmaf(acc, F_IS(c), F_BIAS(c));
+              const float o = fmaf(acc, is_u, bsm[c]);
               if (row_ok && col0 + c < p.out_dim) p.y[(int64_t)row * p.out_dim + col0 + c] = o;
             }
           }
         }
-#undef F_BIAS
-#undef F_IS
         tc_fence_before();
         mbar_arrive(&tempty[b]);
         if (layer < 4) {
@@ -484,6 +507,8 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
           mbar_arrive(&act_ready[n]);
         }
         if (warp == 2 && lane == 0 && slab == (int)blockIdx.x && tl < 16) F_MARK(9 + 2 * tl);  // tile drained
+        if (dbase >= 0 && warp == 17) F_MARK(dbase + 3);
+        if (dbase >= 0 && warp == 9) F_MARK(dbase + 4);
       }
     }
   }
@@ -559,11 +584,20 @@ int mlp_tc_forward(const MlpBlobHeader& h, const void* blob, const float* x, con
     for (int l = 0; l < 4; ++l) { p.bias[l] = F(boff[l]); p.inv_ws[l] = IS(l); }
     p.tcol = tcol; p.t_dev = t_dev; p.t_host = t_host; p.y = y; p.skip = skip;
     p.dbg = tc_debug_buffer();
-    CFM_CUDA_OK(cudaFuncSetAttribute(mlp_fused_h3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFSmemBytes));
+    static int probe = -1;
+    if (probe < 0) { const char* e = getenv("CFM_MLP_PROBE"); probe = e ? atoi(e) : 0; }
+    p.probe = probe;
     int grid = (batch + kTM - 1) / kTM;
     if (grid > sm_count()) grid = sm_count();
-    mlp_fused_h3_kernel<<<grid, kFThreads, kFSmemBytes, s>>>(mx[0], mx[1], mw[0], mw[1], mw[2], mw[3], mw[4], mw[5],
-                                                              mw[6], mw[7], p);
+    if (act == CFM_ACT_SELU) {
+      CFM_CUDA_OK(cudaFuncSetAttribute(mlp_fused_h3_kernel<CFM_ACT_SELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFSmemBytes));
+      mlp_fused_h3_kernel<CFM_ACT_SELU><<<grid, kFThreads, kFSmemBytes, s>>>(mx[0], mx[1], mw[0], mw[1], mw[2], mw[3],
+                                                                              mw[4], mw[5], mw[6], mw[7], p);
+    } else {
+      CFM_CUDA_OK(cudaFuncSetAttribute(mlp_fused_h3_kernel<CFM_ACT_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFSmemBytes));
+      mlp_fused_h3_kernel<CFM_ACT_SILU><<<grid, kFThreads, kFSmemBytes, s>>>(mx[0], mx[1], mw[0], mw[1], mw[2], mw[3],
+                                                                              mw[4], mw[5], mw[6], mw[7], p);
+    }
     ::cfm::note_launches(1);
     CFM_CUDA_OK(cudaGetLastError());
     return CFM_OK;

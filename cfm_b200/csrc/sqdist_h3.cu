@@ -10,10 +10,12 @@
 
 namespace cfm {
 
-// one warp per row; d % 4 == 0, x 16-byte aligned, ldo % 8 == 0
+// one warp per row; d % 4 == 0, x 16-byte aligned, ldo % 8 == 0.  `uniform_absmax` (nullable, device): scale every
+// row by the power of two derived from THIS value instead of the row's own maximum (the MLP weights: one scale per
+// layer, so the epilogue multiplies by a kernel-uniform constant)
 __global__ void prep_rows_h3_kernel(const float* __restrict__ X, int rows, int d, __half* __restrict__ hi,
                                     __half* __restrict__ lo, int64_t ldo, float* __restrict__ sqnorm,
-                                    float* __restrict__ inv_scale) {
+                                    float* __restrict__ inv_scale, const float* __restrict__ uniform_absmax) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -27,6 +29,7 @@ __global__ void prep_rows_h3_kernel(const float* __restrict__ X, int rows, int d
   }
   s = warp_sum(s);
   am = warp_max(am);
+  if (uniform_absmax != nullptr) am = __ldg(uniform_absmax);
   // scale = 2^(13 - floor(log2(am))); non-finite or zero rows keep scale 1 (their products are what they are)
   float sc = 1.f;
   if (am > 0.f && am < 3.0e38f) {
@@ -54,9 +57,28 @@ __global__ void prep_rows_h3_kernel(const float* __restrict__ X, int rows, int d
   }
 }
 
+// max |X| over a (rows x d) matrix into *out (zeroed by the caller)
+__global__ void absmax_h3_kernel(const float* __restrict__ X, int64_t n, float* __restrict__ out) {
+  float am = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = fabsf(X[i]);
+    am = (v <= 3.0e38f) ? fmaxf(am, v) : am;  // non-finite entries do not set the scale
+  }
+  am = warp_max(am);
+  if ((threadIdx.x & 31) == 0) atomic_max_nonneg(out, am);
+}
+
 int prep_rows_h3(const float* X, int rows, int d, __half* hi, __half* lo, int64_t ldo, float* sqnorm,
-                 float* inv_scale, cudaStream_t s) {
-  prep_rows_h3_kernel<<<(rows + 7) / 8, 256, 0, s>>>(X, rows, d, hi, lo, ldo, sqnorm, inv_scale);
+                 float* inv_scale, cudaStream_t s, float* uniform_absmax) {
+  if (uniform_absmax != nullptr) {
+    CFM_CUDA_OK(cudaMemsetAsync(uniform_absmax, 0, sizeof(float), s));
+    const int64_t n = (int64_t)rows * d;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 1024) blocks = 1024;
+    absmax_h3_kernel<<<blocks, 256, 0, s>>>(X, n, uniform_absmax);
+    ::cfm::note_launches(1);
+  }
+  prep_rows_h3_kernel<<<(rows + 7) / 8, 256, 0, s>>>(X, rows, d, hi, lo, ldo, sqnorm, inv_scale, uniform_absmax);
   ::cfm::note_launches(1);
   CFM_CUDA_OK(cudaGetLastError());
   return CFM_OK;
@@ -149,8 +171,8 @@ int sqdist_h3_launch(const float* x0, const float* x1, float* M, int n0, int n1,
   float* isx = reinterpret_cast<float*>(w + W.isx);
   float* isy = reinterpret_cast<float*>(w + W.isy);
   int rc;
-  if ((rc = prep_rows_h3(x0, n0, d, ah, al, W.ld, nx, isx, s)) != CFM_OK) return rc;
-  if ((rc = prep_rows_h3(x1, n1, d, bh, bl, W.ld, ny, isy, s)) != CFM_OK) return rc;
+  if ((rc = prep_rows_h3(x0, n0, d, ah, al, W.ld, nx, isx, s, nullptr)) != CFM_OK) return rc;
+  if ((rc = prep_rows_h3(x1, n1, d, bh, bl, W.ld, ny, isy, s, nullptr)) != CFM_OK) return rc;
   SqDistH3Epilogue epi{M, ldm, nx, ny, isx, isy, cost_max, squared, 0.f, 0.f, 0.f};
   // N tile: 128 (accumulator pairs double-buffered: the read-out of a tile overlaps the MMAs of the next one) or
   // 256 (half the B-operand traffic, but all 512 TMEM columns in use, read-out exposed).  Measured at C2 on the

@@ -91,7 +91,9 @@ class NeuralODE(torch.nn.Module):
         elif self.solver == "euler":
             out = self._euler(mlp, x0, t_span)
         else:
-            out = self._dopri5(mlp, x0, t_span.to(dev).contiguous())
+            # the span stays on the host (where callers build it): the plan keeps a device copy and refreshes it only
+            # when the values change, so a repeated call neither uploads nor reads back anything before the first kernel
+            out = self._dopri5(mlp, x0, t_span.detach().cpu().contiguous())
         return out.reshape(out.shape[0], *shape)
 
     # ------------------------------------------------------------------------------------
@@ -230,6 +232,8 @@ class NeuralODE(torch.nn.Module):
              "t_stage": torch.zeros(1, dtype=torch.float32, device=dev),
              "scratch": torch.zeros(4, dtype=torch.float64, device=dev),
              "pinned": torch.empty(ctypes_sizeof_state(), dtype=torch.uint8, pin_memory=True),
+             "pinned_init": torch.empty(ctypes_sizeof_state(), dtype=torch.uint8, pin_memory=True),
+             "t0": torch.zeros(1, dtype=torch.float32, device=dev), "ts_host": None, "init_graph": None,
              "xs_hi": None, "xs_lo": None, "graph": None, "group": None, "dist": None, "numel_global": B * D,
              "overlap": False}
         off = _ffi.RkState.err_acc.offset  # the float64 accumulator inside the device state struct
@@ -248,43 +252,12 @@ class NeuralODE(torch.nn.Module):
         self._plans[key] = P
         return P
 
-    def _dopri5(self, mlp, x0, t_span):
+    def _enqueue_init(self, mlp, P, lock):
+        """k1 = f(t0, x) and the Hairer initial step (one extra evaluation), enqueued without a host round trip."""
         L = _ffi.lib()
-        dev = x0.device
-        B, D = x0.shape
-        numel = x0.numel()
-        n_span = t_span.numel()
-        sp = _ffi.stream_ptr(dev)
-        ts_host = t_span.cpu()
-        P = self._plan(mlp, B, D, n_span, dev)
-        x, k, xs, traj, st, stp = P["x"], P["k"], P["xs"], P["traj"], P["st"], P["stp"]
-        x.copy_(x0)
-        traj[0].copy_(x0)
-        P["t_span"].copy_(t_span)
-
-        st_host = _ffi.RkState()
-        st_host.t, st_host.t_end = float(ts_host[0]), float(ts_host[-1])
-        st_host.atol, st_host.rtol = self.atol, self.rtol
-        st_host.n_span, st_host.ckpt, st_host.save_slot = n_span, 1, -1
-        st.copy_(torch.frombuffer(bytearray(bytes(st_host)), dtype=torch.uint8), non_blocking=False)
-
-        lock = self.lockstep is not None
-        if lock:
-            import torch.distributed as tdist
-            P["dist"] = tdist
-            P["group"] = None if self.lockstep is True else self.lockstep
-            if not (tdist.is_available() and tdist.is_initialized()):
-                raise RuntimeError("NeuralODE.lockstep needs an initialised torch.distributed process group")
-            cnt = torch.tensor([numel], dtype=torch.int64, device=dev)
-            tdist.all_reduce(cnt, group=P["group"])
-            P["numel_global"] = int(cnt.item())
-            P["group"] = P["group"] if P["group"] is not None else tdist.group.WORLD
-        else:
-            P["group"], P["numel_global"] = None, numel
-        ng = P["numel_global"]
-
-        # k1 = f(t0, x); Hairer initial step needs one extra evaluation
-        mlp.vector_field(st_host.t, x, out=k[0])
+        sp = _ffi.stream_ptr(P["dev"])
+        stp, x, xs, k, numel, ng = P["stp"], P["x"], P["xs"], P["k"], P["numel"], P["numel_global"]
+        mlp.vector_field(P["t0"], x, out=k[0])
         _ffi.check(L.cfm_rk_init_sums(stp, _ffi.ptr(x), _ffi.ptr(k[0]), None, _ffi.ptr(P["scratch"]), numel, 0, sp),
                    "cfm_rk_init_sums")
         if lock:
@@ -301,6 +274,47 @@ class NeuralODE(torch.nn.Module):
         _ffi.check(L.cfm_rk_init_finish(stp, _ffi.ptr(P["t_span"]), _ffi.ptr(P["scratch"]), ng, sp),
                    "cfm_rk_init_finish")
 
+    def _dopri5(self, mlp, x0, ts_host):
+        """``ts_host``: the span as a contiguous fp32 CPU tensor."""
+        dev = x0.device
+        B, D = x0.shape
+        numel = x0.numel()
+        n_span = ts_host.numel()
+        P = self._plan(mlp, B, D, n_span, dev)
+        x, traj, st = P["x"], P["traj"], P["st"]
+        x.copy_(x0)
+        traj[0].copy_(x0)
+        if P["ts_host"] is None or not torch.equal(P["ts_host"], ts_host):
+            P["t_span"].copy_(ts_host)
+            P["t0"].copy_(ts_host[:1])
+            P["ts_host"] = ts_host.clone()
+
+        st_host = _ffi.RkState()
+        st_host.t, st_host.t_end = float(ts_host[0]), float(ts_host[-1])
+        st_host.atol, st_host.rtol = self.atol, self.rtol
+        st_host.n_span, st_host.ckpt, st_host.save_slot = n_span, 1, -1
+        # pinned staging (the previous call ended with a stream synchronize, so the buffer is free): no pageable copy
+        P["pinned_init"].copy_(torch.frombuffer(bytearray(bytes(st_host)), dtype=torch.uint8))
+        st.copy_(P["pinned_init"], non_blocking=True)
+
+        lock = self.lockstep is not None
+        if lock:
+            import torch.distributed as tdist
+            P["dist"] = tdist
+            P["group"] = None if self.lockstep is True else self.lockstep
+            if not (tdist.is_available() and tdist.is_initialized()):
+                raise RuntimeError("NeuralODE.lockstep needs an initialised torch.distributed process group")
+            cnt = torch.tensor([numel], dtype=torch.int64, device=dev)
+            tdist.all_reduce(cnt, group=P["group"])
+            P["numel_global"] = int(cnt.item())
+            P["group"] = P["group"] if P["group"] is not None else tdist.group.WORLD
+        else:
+            P["group"], P["numel_global"] = None, numel
+        if P["init_graph"] is not None and not lock:
+            P["init_graph"].replay()
+        else:
+            self._enqueue_init(mlp, P, lock)
+
         if self.use_cuda_graph and not lock and P["graph"] is None:
             # the step is a fixed kernel sequence whose control flow lives in device memory: capture it
             # once (the eager init above has already loaded every kernel) and replay it per step
@@ -308,6 +322,10 @@ class NeuralODE(torch.nn.Module):
             with torch.cuda.graph(g):
                 self._enqueue_step(mlp, P)
             P["graph"] = g
+            gi = torch.cuda.CUDAGraph()  # the initial-step sequence (2 MLP evaluations + 4 small kernels) likewise
+            with torch.cuda.graph(gi):
+                self._enqueue_init(mlp, P, False)
+            P["init_graph"] = gi
 
         pinned = P["pinned"]
         max_steps = 100000

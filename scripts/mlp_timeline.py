@@ -27,7 +27,7 @@ def report(tag, names):
         if ok.sum() == 0:
             continue
         rel = (col[ok] - t0).float() / 1e3
-        print(f"   {n:<28} median {rel.median():8.1f} us   max {rel.max():8.1f} us")
+        print(f"   {n:<34} median {rel.median():8.2f} us   max {rel.max():8.2f} us")
     dbg.zero_()
 
 
@@ -42,6 +42,9 @@ for tl in range(13):
     n = tl % 2 if tl < 6 else tl - 6
     names += [(8 + 2 * tl, f'L{lay} tile {n} acc ready'), (9 + 2 * tl, f'L{lay} tile {n} drained')]
 names += [(40, 'exit')]
+for base, tag in ((42, 'L1 t0'), (48, 'L2 t0'), (54, 'L4 t0')):
+    names += [(base, tag + ' warp 2 TMEM loads landed'), (base + 1, tag + ' warp 17 past tfull'),
+              (base + 2, tag + ' warp 17 TMEM loads landed'), (base + 3, tag + ' warp 17 done'), (base + 4, tag + ' warp 9 done')]
 with torch.no_grad():
     for _ in range(3):
         m.vector_field(0.3, x)
