@@ -22,6 +22,7 @@
 // epilogues multiply by a kernel-uniform constant; the inv-scale arrays stay per row for the generic core.
 #include "gemm_h3.cuh"
 #include "mlp_common.cuh"
+#include "rk_tableau.h"
 
 namespace cfm {
 
@@ -72,8 +73,18 @@ int mlp_tc_supported(int batch, int dim, int w, int out_dim) {
   // 16-byte aligned fp16 rows for the TMA maps, float4 rows for y; tiny problems stay on the SIMT path
   return batch >= 128 && dim >= 32 && (dim % 8 == 0) && (w % 8 == 0) && w >= 32 && (out_dim % 4 == 0);
 }
+static int fused_mode_on();
 static bool fused_supported(int batch, int dim, int w, int out_dim) {
   return mlp_tc_supported(batch, dim, w, out_dim) && w == 256 && dim >= 64;
+}
+int mlp_tc_rkstage_supported(int batch, int dim, int w, int out_dim) {
+  return fused_supported(batch, dim, w, out_dim) && dim == out_dim && fused_mode_on();
+}
+
+static int fused_mode_on() {  // CFM_MLP_FUSED=0 forces the per-layer launches (A/B experiments)
+  static int m = -1;
+  if (m < 0) { const char* e = getenv("CFM_MLP_FUSED"); m = e ? atoi(e) : 1; }
+  return m;
 }
 
 // x -> fp16 (hi, lo), unscaled and saturating (activation-side operands carry no row scale)
@@ -177,7 +188,7 @@ constexpr int kFActBytes = 2 * kTM * kFW * 2;  // 128 KB: hi [4 chunks x 16 KB] 
 constexpr int kFRingStage = 2 * 128 * kHK * 2; // 32 KB: B_hi | B_lo of one 128 x 64 weight tile
 constexpr int kFRingStages = 3;
 constexpr int kFL1Stage = 2 * kHABytes + 2 * kFW * kHK * 2;  // 96 KB: x_hi | x_lo | W0_hi (256 rows) | W0_lo
-constexpr size_t kFSmemBytes = kFActBytes + kFRingStages * kFRingStage + 256 + kFEpiWarpsC * 32 * 4;
+constexpr size_t kFSmemBytes = kFActBytes + kFRingStages * kFRingStage + 256 + kFEpiWarpsC * 32 * 4 + 256;  // + RkDesc
 constexpr uint32_t kFIdesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);  // M=128, N=128
 
 struct FusedParams {
@@ -192,15 +203,88 @@ struct FusedParams {
   unsigned long long* dbg;  // optional per-CTA globaltimer checkpoints (64 per CTA), see scripts/mlp_timeline.py
   int probe;  // CFM_MLP_PROBE, timing experiments only (results are WRONG when non-zero): bit0 skip the acc1 read-out,
               // bit1 skip the epilogue math and stores
+  // ---- RK mode (template flag): the layer-1 A operand is a dopri5 stage input formed on the fly -------------
+  //   v = x + sum_j (h * coef[j]) k_j   (the same fp32 operations, in the same order, as
+  //   rk_stage_input_kernel), t = t0 + c * h, h and t0 read from the device-resident controller state
+  const float* rk_x;
+  const float* rk_kp[6];  // the rk_n derivative arrays with a non-zero coefficient, ascending j
+  int rk_n;
+  const float* rk_h;    // device scalar: step size
+  const float* rk_t0;   // device scalar: time at the start of the step
+  float rk_coef[6], rk_ecoef[6], rk_c;  // (compacted like rk_kp)
+  float* rk_xnew;       // nullable: fp32 copy of the stage input (stage 6: the candidate state)
+  float* rk_err;        // nullable: sum_j ecoef[j] k_j (first six terms of the embedded error estimate)
 };
 #define F_MARK(slot) do { if (p.dbg) p.dbg[blockIdx.x * 64 + (slot)] = tc_now(); } while (0)
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+
+// RK mode, one 64-column chunk of the layer-1 A operand (128 rows): 512 threads; thread = (float4 column group f of
+// the chunk, rows rb + 32 i).  A warp reads two 256-byte row segments per array (fully coalesced) and writes two
+// 128-byte swizzled rows of the hi tile and of the lo tile (conflict-free 64-bit stores).  NA = number of derivative
+// arrays in the combination (compile-time: straight-line loads, no predicates); RU rows per pass keep >= 6 128-bit
+// loads in flight per thread.
+struct RkDesc {  // shared-memory copy of the RK-mode arguments (pointers indexed by unrolled loops stay out of registers)
+  const float* x;
+  const float* kp[6];
+  float* xnew;
+  float* err;
+  float coef[6], ecoef[6];
+  int batch, dim;
+};
+template <int NA>
+__device__ __forceinline__ void rk_fill_chunk(const RkDesc& p, float h, uint8_t* sb, int64_t row0, int col,
+                                              bool col_ok, int rb, int f) {
+  constexpr int RU = NA <= 2 ? 4 : (NA <= 4 ? 2 : 1);
+#pragma unroll 1
+  for (int r0 = 0; r0 < 4; r0 += RU) {
+    float4 v[RU], kk[RU][NA > 0 ? NA : 1];
+    bool ok[RU];
+    // straight-line code: out-of-range rows / columns load element 0 (always valid) and are zeroed afterwards -- a
+    // branch around the loads would push the arrays into local memory
+#pragma unroll
+    for (int q = 0; q < RU; ++q) {
+      const int r = rb + 32 * (r0 + q);
+      ok[q] = col_ok && row0 + r < p.batch;
+      const int64_t idx = ok[q] ? (row0 + r) * p.dim + col : 0;
+      v[q] = __ldg(reinterpret_cast<const float4*>(p.x + idx));
+#pragma unroll
+      for (int a = 0; a < NA; ++a) kk[q][a] = __ldg(reinterpret_cast<const float4*>(p.kp[a] + idx));
+    }
+#pragma unroll
+    for (int q = 0; q < RU; ++q) {
+      const int r = rb + 32 * (r0 + q);
+      float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        const float aj = h * p.coef[a];
+        v[q].x = fmaf(aj, kk[q][a].x, v[q].x); v[q].y = fmaf(aj, kk[q][a].y, v[q].y);
+        v[q].z = fmaf(aj, kk[q][a].z, v[q].z); v[q].w = fmaf(aj, kk[q][a].w, v[q].w);
+        e.x = fmaf(p.ecoef[a], kk[q][a].x, e.x); e.y = fmaf(p.ecoef[a], kk[q][a].y, e.y);
+        e.z = fmaf(p.ecoef[a], kk[q][a].z, e.z); e.w = fmaf(p.ecoef[a], kk[q][a].w, e.w);
+      }
+      if (ok[q]) {
+        const int64_t idx = (row0 + r) * p.dim + col;
+        if (p.xnew != nullptr) *reinterpret_cast<float4*>(p.xnew + idx) = v[q];
+        if (p.err != nullptr) *reinterpret_cast<float4*>(p.err + idx) = e;
+      } else {
+        v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      uint32_t h0, l0, h1, l1;
+      split_h3_sat_x2(v[q].x, v[q].y, h0, l0);
+      split_h3_sat_x2(v[q].z, v[q].w, h1, l1);
+      const int off = r * 128 + (((f >> 1) ^ (r & 7)) << 4) + ((f & 1) << 3);
+      *reinterpret_cast<uint2*>(sb + off) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(sb + kHABytes + off) = make_uint2(l0, l1);
+    }
+  }
+}
+
 constexpr int kFEpiWarps = kFEpiWarpsC;          // four per TMEM lane quadrant, one 32-column chunk each
 constexpr int kFThreads = 64 + 32 * kFEpiWarps;  // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 
-template <int ACT>
+template <int ACT, bool RK>
 __global__ void __launch_bounds__(kFThreads, 1)
 mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                     const __grid_constant__ CUtensorMap map_w0h, const __grid_constant__ CUtensorMap map_w0l,
@@ -222,6 +306,7 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
   uint64_t* slab_done = bars + 16;   // [1] every MMA of the slab has retired
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 17);
   float* bias_sm = reinterpret_cast<float*>(smem + kFActBytes + kFRingStages * kFRingStage + 256);  // [16 warps][32]
+  RkDesc* rkd = reinterpret_cast<RkDesc*>(smem + kFActBytes + kFRingStages * kFRingStage + 256 + kFEpiWarpsC * 32 * 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p.skip != nullptr && __ldg(p.skip) != 0) return;  // uniform over the grid; nothing has been allocated yet
@@ -231,8 +316,15 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
   const int t4 = (p.out_dim + 127) / 128;   // layer-4 tiles
   const int tiles_per_slab = 6 + t4;
 
+  if (RK && threadIdx.x == 32) {
+    rkd->x = p.rk_x; rkd->xnew = p.rk_xnew; rkd->err = p.rk_err; rkd->batch = p.batch; rkd->dim = p.dim;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { rkd->kp[j] = p.rk_kp[j]; rkd->coef[j] = p.rk_coef[j]; rkd->ecoef[j] = p.rk_ecoef[j]; }
+  }
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(&l1_full[s], 1); mbar_init(&l1_empty[s], 1); }
+    // RK mode: a layer-1 stage is complete when the W0 tiles have landed (TMA transaction bytes, one arrive by the
+    // producer) AND every epilogue thread has written its share of the stage-input tile
+    for (int s = 0; s < 2; ++s) { mbar_init(&l1_full[s], RK ? 1 + 32 * kFEpiWarps : 1); mbar_init(&l1_empty[s], 1); }
     for (int s = 0; s < kFRingStages; ++s) { mbar_init(&r_full[s], 1); mbar_init(&r_empty[s], 1); }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
@@ -267,9 +359,11 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
           const int s = q1 & 1;
           mbar_wait(&l1_empty[s], ((q1 >> 1) & 1) ^ 1);
           uint8_t* sb = s == 0 ? act : ring;
-          mbar_expect_tx(&l1_full[s], kFL1Stage);
-          tma_load_2d(sb, &map_xh, &l1_full[s], kc * kHK, slab * kTM);
-          tma_load_2d(sb + kHABytes, &map_xl, &l1_full[s], kc * kHK, slab * kTM);
+          mbar_expect_tx(&l1_full[s], RK ? kFL1Stage - 2 * kHABytes : kFL1Stage);
+          if (!RK) {
+            tma_load_2d(sb, &map_xh, &l1_full[s], kc * kHK, slab * kTM);
+            tma_load_2d(sb + kHABytes, &map_xl, &l1_full[s], kc * kHK, slab * kTM);
+          }
           tma_load_2d(sb + 2 * kHABytes, &map_w0h, &l1_full[s], kc * kHK, 0);
           tma_load_2d(sb + 2 * kHABytes + kFW * kHK * 2, &map_w0l, &l1_full[s], kc * kHK, 0);
         }
@@ -386,9 +480,38 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
     const int part = (warp - 2) >> 2;   // 32-column chunk of the 128-column tile
     const int r_in = quad * 32 + lane;  // row inside the slab
     uint32_t g = 0;
+    uint32_t q1e = 0;  // RK mode: running layer-1 chunk counter (stage = q1e & 1)
     for (int slab = blockIdx.x; slab < num_slabs; slab += gridDim.x) {
       const int row = slab * kTM + r_in;
-      const float t = p.tcol ? (p.t_dev ? __ldg(p.t_dev) : p.t_host) : 0.f;
+      float t = 0.f;
+      if (RK) {
+        const float h = __ldg(p.rk_h);
+        t = fmaf(p.rk_c, h, __ldg(p.rk_t0));
+        // ---- layer-1 A operand: the stage input of this slab, formed chunk by chunk while the MMAs of the previous
+        // chunk run (rk_fill_chunk)
+        const int te = (int)threadIdx.x - 64, f = te & 15, rb = te >> 4;
+        for (int kc = 0; kc < nk1; ++kc, ++q1e) {
+          const int s = q1e & 1;
+          mbar_wait(&l1_empty[s], ((q1e >> 1) & 1) ^ 1);
+          uint8_t* sb = s == 0 ? act : ring;
+          const int col = kc * kHK + 4 * f;
+          const bool col_ok = col < p.dim;  // dim % 4 == 0: a float4 is entirely inside or outside
+          const int64_t row0 = (int64_t)slab * kTM;
+          switch (p.rk_n) {
+            case 0: rk_fill_chunk<0>(*rkd, h, sb, row0, col, col_ok, rb, f); break;
+            case 1: rk_fill_chunk<1>(*rkd, h, sb, row0, col, col_ok, rb, f); break;
+            case 2: rk_fill_chunk<2>(*rkd, h, sb, row0, col, col_ok, rb, f); break;
+            case 3: rk_fill_chunk<3>(*rkd, h, sb, row0, col, col_ok, rb, f); break;
+            case 4: rk_fill_chunk<4>(*rkd, h, sb, row0, col, col_ok, rb, f); break;
+            case 5: rk_fill_chunk<5>(*rkd, h, sb, row0, col, col_ok, rb, f); break;
+            default: rk_fill_chunk<6>(*rkd, h, sb, row0, col, col_ok, rb, f); break;
+          }
+          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core's async proxy
+          mbar_arrive(&l1_full[s]);
+        }
+      } else {
+        t = p.tcol ? (p.t_dev ? __ldg(p.t_dev) : p.t_host) : 0.f;
+      }
       for (int tl = 0; tl < tiles_per_slab; ++tl, ++g) {
         const int layer = tl < 6 ? (tl >> 1) + 1 : 4;
         const int n = tl < 6 ? (tl & 1) : tl - 6;
@@ -536,15 +659,9 @@ static H3MlpWs h3_mlp_ws(int batch, int dim, int w) {
 }
 size_t mlp_tc_workspace_bytes(int batch, int dim, int w, int) { return h3_mlp_ws(batch, dim, w).total; }
 
-static int fused_mode() {  // CFM_MLP_FUSED=0 forces the per-layer launches (A/B experiments)
-  static int m = -1;
-  if (m < 0) { const char* e = getenv("CFM_MLP_FUSED"); m = e ? atoi(e) : 1; }
-  return m;
-}
-
 int mlp_tc_forward(const MlpBlobHeader& h, const void* blob, const float* x, const void* x_hi_v,
                    const void* x_lo_v, int batch, const float* t_dev, float t_host, int act, float* y, void* ws,
-                   size_t ws_bytes, const int32_t* skip, cudaStream_t s) {
+                   size_t ws_bytes, const int32_t* skip, const MlpRkStage* rk, cudaStream_t s) {
   const H3MlpWs W = h3_mlp_ws(batch, h.dim, h.w);
   CFM_REQUIRE(ws_bytes >= W.total, "mlp tcgen05: workspace too small (%zu < %zu)", ws_bytes, W.total);
   CFM_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x_hi_v) | reinterpret_cast<uintptr_t>(x_lo_v) |
@@ -562,17 +679,26 @@ int mlp_tc_forward(const MlpBlobHeader& h, const void* blob, const float* x, con
   int rc;
   const __half* xh = reinterpret_cast<const __half*>(x_hi_v);
   const __half* xl = reinterpret_cast<const __half*>(x_lo_v);
-  if (xh == nullptr) {  // plain fp32 input: split it here; otherwise the caller (the RK stage kernel) already did
+  if (rk != nullptr) {
+    CFM_REQUIRE(mlp_tc_rkstage_supported(batch, h.dim, h.w, h.out_dim), "mlp tcgen05: shape has no fused RK-stage path");
+    CFM_REQUIRE(h.time_varying && rk->x && rk->k && rk->h_dev && rk->t0_dev && rk->numel == (int64_t)batch * h.dim,
+                "mlp tcgen05: bad RK-stage arguments");
+    CFM_REQUIRE(((reinterpret_cast<uintptr_t>(rk->x) | reinterpret_cast<uintptr_t>(rk->k) |
+                  reinterpret_cast<uintptr_t>(rk->xnew) | reinterpret_cast<uintptr_t>(rk->err)) & 15) == 0,
+                "mlp tcgen05: RK-stage arrays must be 16-byte aligned");
+  } else if (xh == nullptr) {  // plain fp32 input: split it here; otherwise the caller (the RK stage kernel) already did
     if ((rc = split_h3_launch(x, Hp(W.xh), Hp(W.xl), (int64_t)batch * h.dim, s)) != CFM_OK) return rc;
     xh = Hp(W.xh); xl = Hp(W.xl);
   }
   const float* tcol = h.time_varying ? F(h.off_w0t) : nullptr;
   const int64_t boff[4] = {h.off_b0, h.off_b1, h.off_b2, h.off_b3};
 
-  if (fused_mode() && fused_supported(batch, h.dim, h.w, h.out_dim)) {
+  if (fused_mode_on() && fused_supported(batch, h.dim, h.w, h.out_dim)) {
     CUtensorMap mx[2], mw[8];
-    if ((rc = tc_make_map_f16(&mx[0], xh, batch, h.dim, (int64_t)h.dim, kTM)) != CFM_OK) return rc;
-    if ((rc = tc_make_map_f16(&mx[1], xl, batch, h.dim, (int64_t)h.dim, kTM)) != CFM_OK) return rc;
+    if (rk == nullptr) {
+      if ((rc = tc_make_map_f16(&mx[0], xh, batch, h.dim, (int64_t)h.dim, kTM)) != CFM_OK) return rc;
+      if ((rc = tc_make_map_f16(&mx[1], xl, batch, h.dim, (int64_t)h.dim, kTM)) != CFM_OK) return rc;
+    }
     const int rows[4] = {h.w, h.w, h.w, h.out_dim}, cols[4] = {h.dim, h.w, h.w, h.w};
     for (int l = 0; l < 4; ++l) {
       const int box = l == 0 ? 256 : 128;
@@ -587,22 +713,42 @@ int mlp_tc_forward(const MlpBlobHeader& h, const void* blob, const float* x, con
     static int probe = -1;
     if (probe < 0) { const char* e = getenv("CFM_MLP_PROBE"); probe = e ? atoi(e) : 0; }
     p.probe = probe;
+    p.rk_x = nullptr; p.rk_n = 0; p.rk_h = nullptr; p.rk_t0 = nullptr; p.rk_c = 0.f;
+    p.rk_xnew = nullptr; p.rk_err = nullptr;
+    for (int j = 0; j < 6; ++j) { p.rk_kp[j] = nullptr; p.rk_coef[j] = 0.f; p.rk_ecoef[j] = 0.f; }
+    if (rk != nullptr) {
+      p.rk_x = rk->x; p.rk_h = rk->h_dev; p.rk_t0 = rk->t0_dev; p.rk_c = rk->c;
+      p.rk_xnew = rk->xnew; p.rk_err = rk->err;
+      for (int j = 0; j < 6; ++j)
+        if (rk->coef[j] != 0.f) {  // zero coefficients contribute nothing (and are skipped by cfm_rk_stage_input too)
+          p.rk_kp[p.rk_n] = rk->k + (int64_t)j * rk->numel;
+          p.rk_coef[p.rk_n] = rk->coef[j];
+          p.rk_ecoef[p.rk_n] = rk->ecoef[j];
+          ++p.rk_n;
+        }
+      mx[0] = mw[0]; mx[1] = mw[1];  // the A maps are not used: the stage input is formed inside the kernel
+    }
     int grid = (batch + kTM - 1) / kTM;
     if (grid > sm_count()) grid = sm_count();
+#define CFM_LAUNCH_FUSED(ACT_, RK_)                                                                                   \
+    do {                                                                                                              \
+      CFM_CUDA_OK(cudaFuncSetAttribute(mlp_fused_h3_kernel<ACT_, RK_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                       (int)kFSmemBytes));                                                            \
+      mlp_fused_h3_kernel<ACT_, RK_><<<grid, kFThreads, kFSmemBytes, s>>>(mx[0], mx[1], mw[0], mw[1], mw[2], mw[3],   \
+                                                                          mw[4], mw[5], mw[6], mw[7], p);             \
+    } while (0)
     if (act == CFM_ACT_SELU) {
-      CFM_CUDA_OK(cudaFuncSetAttribute(mlp_fused_h3_kernel<CFM_ACT_SELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFSmemBytes));
-      mlp_fused_h3_kernel<CFM_ACT_SELU><<<grid, kFThreads, kFSmemBytes, s>>>(mx[0], mx[1], mw[0], mw[1], mw[2], mw[3],
-                                                                              mw[4], mw[5], mw[6], mw[7], p);
+      if (rk) CFM_LAUNCH_FUSED(CFM_ACT_SELU, true); else CFM_LAUNCH_FUSED(CFM_ACT_SELU, false);
     } else {
-      CFM_CUDA_OK(cudaFuncSetAttribute(mlp_fused_h3_kernel<CFM_ACT_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFSmemBytes));
-      mlp_fused_h3_kernel<CFM_ACT_SILU><<<grid, kFThreads, kFSmemBytes, s>>>(mx[0], mx[1], mw[0], mw[1], mw[2], mw[3],
-                                                                              mw[4], mw[5], mw[6], mw[7], p);
+      if (rk) CFM_LAUNCH_FUSED(CFM_ACT_SILU, true); else CFM_LAUNCH_FUSED(CFM_ACT_SILU, false);
     }
+#undef CFM_LAUNCH_FUSED
     ::cfm::note_launches(1);
     CFM_CUDA_OK(cudaGetLastError());
     return CFM_OK;
   }
 
+  CFM_REQUIRE(rk == nullptr, "mlp tcgen05: the RK-stage form needs the fused kernel");
   // per-layer launches of the generic core
   MlpH3Epilogue e0{F(boff[0]), IS(0), tcol, t_dev, t_host, act, nullptr, Hp(W.ah), Hp(W.al), (int64_t)h.w, 0.f};
   if ((rc = launch_gemm_h3<128>(xh, xl, batch, (int64_t)h.dim, WH(0), WL(0), h.w, tb.ld[0], h.dim, e0, s)) != CFM_OK) return rc;

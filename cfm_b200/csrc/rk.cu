@@ -14,6 +14,7 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "rk_tableau.h"
 
 namespace cfm {
 
@@ -26,21 +27,10 @@ __device__ __forceinline__ void rk_split_h3(float v, __half& hi, __half& lo) {
 }
 
 
-__constant__ float kC[7] = {0.f, 1.f / 5, 3.f / 10, 4.f / 5, 8.f / 9, 1.f, 1.f};
-__constant__ float kA[7][6] = {
-    {0, 0, 0, 0, 0, 0},
-    {1.f / 5, 0, 0, 0, 0, 0},
-    {3.f / 40, 9.f / 40, 0, 0, 0, 0},
-    {44.f / 45, -56.f / 15, 32.f / 9, 0, 0, 0},
-    {19372.f / 6561, -25360.f / 2187, 64448.f / 6561, -212.f / 729, 0, 0},
-    {9017.f / 3168, -355.f / 33, 46732.f / 5247, 49.f / 176, -5103.f / 18656, 0},
-    {35.f / 384, 0.f, 500.f / 1113, 125.f / 192, -2187.f / 6784, 11.f / 84}};
+__constant__ float kC[7] = CFM_RK_C_INIT;
+__constant__ float kA[7][6] = CFM_RK_A_INIT;
 // b5 - b4 (embedded error weights), k1..k7
-__constant__ float kE[7] = {(float)(35.0 / 384 - 1951.0 / 21600), 0.f,
-                            (float)(500.0 / 1113 - 22642.0 / 50085),
-                            (float)(125.0 / 192 - 451.0 / 720),
-                            (float)(-2187.0 / 6784 + 12231.0 / 42400),
-                            (float)(11.0 / 84 - 649.0 / 6300), (float)(-1.0 / 60)};
+__constant__ float kE[7] = CFM_RK_E_INIT;
 
 static inline int ew_grid(int64_t numel) {
   int64_t blocks = (numel / 4 + 255) / 256 + 1;
@@ -69,7 +59,7 @@ __global__ void rk_stage_input_kernel(const cfm_rk_state* __restrict__ st, const
                                       int stage) {
   if (st->done) return;
   const float dt = st->dt;
-  if (blockIdx.x == 0 && threadIdx.x == 0 && t_stage) *t_stage = st->t + kC[stage] * dt;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && t_stage) *t_stage = fmaf(kC[stage], dt, st->t);
   float a[6];
 #pragma unroll
   for (int j = 0; j < 6; ++j) a[j] = dt * kA[stage][j];
@@ -128,7 +118,7 @@ __global__ void rk_stage_partial_kernel(const cfm_rk_state* __restrict__ st, con
                                         int stage) {
   if (st->done) return;
   const float dt = st->dt;
-  if (blockIdx.x == 0 && threadIdx.x == 0 && t_stage) *t_stage = st->t + kC[stage] * dt;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && t_stage) *t_stage = fmaf(kC[stage], dt, st->t);
   float a[6];
 #pragma unroll
   for (int j = 0; j < 6; ++j) a[j] = dt * kA[stage][j];

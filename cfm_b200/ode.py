@@ -63,6 +63,10 @@ class NeuralODE(torch.nn.Module):
         # same box): the partial kernels compete with the MLP's operand feed for L2 / HBM bandwidth and the finish
         # kernels add launches -- so the default is the one-piece stage input on one stream.
         self.overlap_stages = False
+        # True (default): a stage evaluation is ONE launch -- the stage input x + dt sum a_sj k_j is formed inside the
+        # fused MLP kernel as its layer-1 operand producer (cfm_mlp_forward_rkstage_f32; bit-identical to the separate
+        # stage-input kernel, which remains the path of other widths and of fuse_stage_input = False)
+        self.fuse_stage_input = True
         self._plans = {}
 
     @torch.no_grad()
@@ -146,9 +150,12 @@ class NeuralODE(torch.nn.Module):
         sp = _ffi.stream_ptr(P["dev"])
         stp, x, xnew, xs, k, numel = P["stp"], P["x"], P["xnew"], P["xs"], P["k"], P["numel"]
         split = P["xs_hi"] is not None
-        if split and P["overlap"]:
+        if P["rkfused"]:
+            for stage in range(1, 7):  # stage input + evaluation in one launch; stage 6 leaves xnew and the error partial
+                mlp.vector_field_rkstage(P["st"], x, k, stage, xnew if stage == 6 else None, xs if stage == 6 else None)
+        elif split and P["overlap"]:
             self._enqueue_stages_overlapped(mlp, P)
-        for stage in range(1, 7) if not (split and P["overlap"]) else ():
+        for stage in range(1, 7) if not (P["rkfused"] or (split and P["overlap"])) else ():
             out = xs if stage < 6 else xnew
             if split:
                 # the stage input goes straight to the MLP as its TF32 operand pair; only stage 6
@@ -163,7 +170,7 @@ class NeuralODE(torch.nn.Module):
                                                 _ffi.ptr(P["t_stage"]), None, numel, stage, sp), "cfm_rk_stage_input")
                 mlp.vector_field(P["t_stage"], out, out=k[stage])
         _ffi.check(L.cfm_rk_error_norm(stp, _ffi.ptr(x), _ffi.ptr(xnew), _ffi.ptr(k),
-                                       _ffi.ptr(xs if split else None), numel, sp), "cfm_rk_error_norm")
+                                       _ffi.ptr(xs if (split or P["rkfused"]) else None), numel, sp), "cfm_rk_error_norm")
         if P["group"] is not None:  # lock-step: the error norm is over the rows of ALL ranks
             P["dist"].all_reduce(P["err_acc"], group=P["group"])
         _ffi.check(L.cfm_rk_control(stp, _ffi.ptr(P["t_span"]), P["numel_global"], sp), "cfm_rk_control")
@@ -216,7 +223,7 @@ class NeuralODE(torch.nn.Module):
     def _plan(self, mlp, B, D, n_span, dev):
         """Persistent buffers (+ the captured step graph) for one problem shape and weight version."""
         key = (id(mlp), B, D, n_span, str(dev), mlp._weights_key(), mlp.mlp_algo, mlp.act, self.lockstep is not None,
-               self.overlap_stages)
+               self.overlap_stages, self.fuse_stage_input)
         P = self._plans.get(key)
         if P is not None:
             return P
@@ -235,7 +242,7 @@ class NeuralODE(torch.nn.Module):
              "pinned_init": torch.empty(ctypes_sizeof_state(), dtype=torch.uint8, pin_memory=True),
              "t0": torch.zeros(1, dtype=torch.float32, device=dev), "ts_host": None, "init_graph": None,
              "xs_hi": None, "xs_lo": None, "graph": None, "group": None, "dist": None, "numel_global": B * D,
-             "overlap": False}
+             "overlap": False, "rkfused": False}
         off = _ffi.RkState.err_acc.offset  # the float64 accumulator inside the device state struct
         P["err_acc"] = st[off:off + 8].view(torch.float64)
         off = _ffi.RkState.done.offset  # int32: non-zero once t has reached t_end
@@ -244,6 +251,7 @@ class NeuralODE(torch.nn.Module):
             # stage inputs go to the MLP as its fp16x3 tensor-core operand pair (hi, lo), written by the RK kernel
             P["xs_hi"] = torch.empty((B, D), dtype=torch.float16, device=dev)
             P["xs_lo"] = torch.empty((B, D), dtype=torch.float16, device=dev)
+            P["rkfused"] = bool(self.fuse_stage_input and not self.overlap_stages and mlp.rkstage_path(B))
             if self.overlap_stages and (B * D) % 4 == 0:
                 P["overlap"] = True
                 P["side"] = torch.cuda.Stream(dev)

@@ -271,6 +271,20 @@ int cfm_rk_stage_partial(const cfm_rk_state* st, const float* x, const float* k,
                          float* err_partial, float* t_stage, int64_t numel, int stage, void* stream);
 int cfm_rk_stage_finish(const cfm_rk_state* st, const float* partial, const float* k, float* out, void* out_hi,
                         void* out_lo, float* err_partial, int64_t numel, int stage, void* stream);
+/* One dopri5 stage EVALUATION in one launch (256-wide vector-field MLPs with out_dim == dim; cfm_mlp_rkstage_supported()
+ * != 0 tells whether a shape qualifies):  k_{stage+1} = f(t + c[stage] dt, x + dt sum_{j<stage} a[stage][j] k_j).
+ * The stage input is formed INSIDE the fused MLP kernel, as the layer-1 operand producer (the same fp32 operations in
+ * the same order as cfm_rk_stage_input, hence bit-identical results), so it neither makes a separate pass over
+ * x, k_1..k_stage nor round-trips through HBM as an fp16 pair.  k: the 7 contiguous derivative arrays (k_{stage+1} =
+ * k + stage * batch * dim is written); xnew (nullable) receives the fp32 stage input (stage 6: the candidate state),
+ * err_partial (nullable, stage 6 only) the first six terms of the embedded error estimate.  Returns at once when
+ * st->done != 0.  `prepared` must have been built with time_varying = 1.  Replaces, per NFE, the reference's
+ * torch.cat([x, t]) + 4 nn.Linear + 3 SELU (torchcfm/utils.py:51-52, models/models.py:10-21) and torchdyn's stage
+ * combination. */
+int cfm_mlp_rkstage_supported(int batch, int dim, int w, int out_dim);
+int cfm_mlp_forward_rkstage_f32(const void* prepared, const cfm_rk_state* st, const float* x, float* k, int stage,
+                                float* xnew, float* err_partial, int batch, int dim, int w, int out_dim, int act,
+                                void* workspace, size_t workspace_bytes, void* stream);
 /* st->err_acc += sum((dt*sum_j e_j k_j / (atol + rtol*max(|x|,|xnew|)))^2); with err_partial (see above) the
  * sum over j is err_partial + e_7 k_7 */
 int cfm_rk_error_norm(cfm_rk_state* st, const float* x, const float* xnew, const float* k,

@@ -387,3 +387,67 @@ def test_dopri5_overlapped_stage_inputs_equal_the_serial_driver():
     for o, s in outs[1:]:
         assert torch.equal(o, outs[0][0])
         assert (s["nfe"], s["accepted"], s["rejected"]) == (outs[0][1]["nfe"], outs[0][1]["accepted"], outs[0][1]["rejected"])
+
+
+@pytest.mark.parametrize("B,dim,act", [(1500, 64, "selu"), (1000, 784, "selu"), (300, 200, "silu")])
+def test_dopri5_stage_input_formed_inside_the_fused_mlp_equals_the_separate_kernel(B, dim, act):
+    """cfm_mlp_forward_rkstage_f32 (stage input formed by the fused MLP kernel's layer-1 operand producer, one launch per
+    NFE) against the two-launch form (cfm_rk_stage_input + cfm_mlp_forward_split_gated_f32): the same fp32 operations
+    in the same order, so trajectories, step counts and the controller's error ratios are bit-identical -- on ragged
+    slabs (B % 128 != 0), a ragged last K chunk (784 = 12 x 64 + 16; 200 = 3 x 64 + 8) and both activations."""
+    torch.manual_seed(3)
+    m = cfm_b200.MLP(dim=dim, w=256, time_varying=True).to(DEV)
+    if act == "silu":
+        m.act = _ffi.ACT_SILU
+    x = torch.randn(B, dim, generator=torch.Generator().manual_seed(4)).to(DEV)
+    span = torch.linspace(0, 1, 3)
+    outs = []
+    for fuse, graph in ((False, True), (True, True), (True, False)):
+        node = cfm_b200.NeuralODE(cfm_b200.torch_wrapper(m), solver="dopri5", atol=1e-5, rtol=1e-5)
+        node.fuse_stage_input, node.use_cuda_graph = fuse, graph
+        node.trajectory(x, span)
+        outs.append((node.trajectory(x, span).clone(), dict(node.stats)))
+        P = next(iter(node._plans.values()))
+        assert P["rkfused"] == fuse
+    for o, s in outs[1:]:
+        assert torch.equal(o, outs[0][0])
+        assert (s["nfe"], s["accepted"], s["rejected"], s["last_ratio"]) == \
+            (outs[0][1]["nfe"], outs[0][1]["accepted"], outs[0][1]["rejected"], outs[0][1]["last_ratio"])
+
+
+def test_rkstage_single_evaluation_against_the_float64_oracle():
+    """One stage evaluation through the one-launch form, checked directly: k_{s+1}, xnew and the error partial against
+    float64 arithmetic on the same inputs (1e-5 of max|y| for the field, fp32 rounding for the combinations)."""
+    from oracle import vector_field as vf
+    torch.manual_seed(5)
+    B, D = 777, 784
+    m = cfm_b200.MLP(dim=D, w=256, time_varying=True)
+    sd = {k_: v_.clone() for k_, v_ in m.state_dict().items()}
+
+    def f64(t, z):  # utils.py:51-52 + models.py:20-21 in float64
+        return vf.mlp_forward_from_state(sd, torch.cat([z.double(), torch.full((z.shape[0], 1), t, dtype=torch.float64)], 1))
+    m = m.to(DEV)
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(B, D, generator=g)
+    k = torch.randn(7, B, D, generator=g)
+    st = _ffi.RkState()
+    st.t, st.dt, st.t_end, st.atol, st.rtol = 0.25, 0.125, 1.0, 1e-4, 1e-4
+    std = torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8).to(DEV)
+    A6 = [35 / 384, 0.0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84]
+    E = [35 / 384 - 1951 / 21600, 0.0, 500 / 1113 - 22642 / 50085, 125 / 192 - 451 / 720,
+         -2187 / 6784 + 12231 / 42400, 11 / 84 - 649 / 6300]
+    xd, kd = x.to(DEV), k.to(DEV).contiguous()
+    xnew, errp = torch.zeros(B, D, device=DEV), torch.zeros(B, D, device=DEV)
+    m.vector_field_rkstage(std, xd, kd, 6, xnew, errp)
+    xs = x.double() + 0.125 * sum(a * k[j].double() for j, a in enumerate(A6))
+    ep = sum(e * k[j].double() for j, e in enumerate(E))
+    assert (xnew.cpu().double() - xs).abs().max() <= 4e-6 * xs.abs().max()
+    assert (errp.cpu().double() - ep).abs().max() <= 4e-6 * max(1.0, ep.abs().max().item())
+    ref = f64(0.25 + 1.0 * 0.125, xnew.cpu())
+    got = kd[6].cpu().double()
+    assert (got - ref).abs().max() <= 1e-5 * ref.abs().max()
+    # stage 2 (two derivative arrays, c = 3/10), no side outputs
+    m.vector_field_rkstage(std, xd, kd, 2)
+    xs2 = (x.double() + 0.125 * (3 / 40 * k[0].double() + 9 / 40 * k[1].double())).float()
+    ref2 = f64(float(np.float32(0.25) + np.float32(0.3) * np.float32(0.125)), xs2)
+    assert (kd[2].cpu().double() - ref2).abs().max() <= 1e-5 * ref2.abs().max()
