@@ -212,6 +212,8 @@ struct FusedParams {
   const float* rk_h;    // device scalar: step size
   const float* rk_t0;   // device scalar: time at the start of the step
   float rk_coef[6], rk_ecoef[6], rk_c;  // (compacted like rk_kp)
+  int rk_pf;            // L2 prefetch distance in 64-column chunks (CFM_RK_PF, default 2; 0 = off)
+  int rk_ldmode;        // CFM_RK_LD: 0 __ldg, 1 nc + L1::no_allocate, 2 ld.global.cg
   float* rk_xnew;       // nullable: fp32 copy of the stage input (stage 6: the candidate state)
   float* rk_err;        // nullable: sum_j ecoef[j] k_j (first six terms of the embedded error estimate)
 };
@@ -231,12 +233,45 @@ struct RkDesc {  // shared-memory copy of the RK-mode arguments (pointers indexe
   float* xnew;
   float* err;
   float coef[6], ecoef[6];
-  int batch, dim;
+  int batch, dim, n, ldmode;
 };
+// 128-bit global load of the RK producer.  With 224 KB of shared memory carved out the L1 is ~28 KB, and lines
+// allocated for in-flight loads bound the bytes a plain (allocating) load stream keeps in flight to about that much:
+// measured 22 GB/s per SM.  mode 1: read-only path without L1 allocation; mode 2: ld.global.cg (L2 only); 0: __ldg.
+__device__ __forceinline__ float4 rk_ld(const float* ptr, int mode) {
+  float4 v;
+  if (mode == 1) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr));
+  } else if (mode == 2) {
+    v = __ldcg(reinterpret_cast<const float4*>(ptr));
+  } else {
+    v = __ldg(reinterpret_cast<const float4*>(ptr));
+  }
+  return v;
+}
+// fire-and-forget L2 prefetch of a contiguous global range (no shared memory, no completion tracking)
+__device__ __forceinline__ void rk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+// The register file bounds how many loads the 512 producer threads keep in flight (<= 12 x 16 B each), far less than
+// the bandwidth-delay product of HBM; so every chunk is first pulled into L2 two chunks ahead -- one bulk prefetch per
+// (array, row): thread = (row te & 127, arrays te >> 7, te >> 7 + 4) -- and the loads that feed the arithmetic see L2
+// latency only.
+__device__ __forceinline__ void rk_prefetch_chunk(const RkDesc& p, int64_t row0, int kc, int te) {
+  const int64_t grow = row0 + (te & 127);
+  const int col = kc * kHK;
+  if (grow < p.batch && col < p.dim) {
+    const uint32_t bytes = (uint32_t)min(kHK, p.dim - col) * 4u;
+    for (int a = te >> 7; a <= p.n; a += 4)
+      rk_prefetch_l2((a == 0 ? p.x : p.kp[a - 1]) + grow * p.dim + col, bytes);
+  }
+}
 template <int NA>
 __device__ __forceinline__ void rk_fill_chunk(const RkDesc& p, float h, uint8_t* sb, int64_t row0, int col,
                                               bool col_ok, int rb, int f) {
-  constexpr int RU = NA <= 2 ? 4 : (NA <= 4 ? 2 : 1);
+  constexpr int RU = NA <= 2 ? 4 : 2;
+  const int ldmode = p.ldmode;
 #pragma unroll 1
   for (int r0 = 0; r0 < 4; r0 += RU) {
     float4 v[RU], kk[RU][NA > 0 ? NA : 1];
@@ -248,9 +283,9 @@ __device__ __forceinline__ void rk_fill_chunk(const RkDesc& p, float h, uint8_t*
       const int r = rb + 32 * (r0 + q);
       ok[q] = col_ok && row0 + r < p.batch;
       const int64_t idx = ok[q] ? (row0 + r) * p.dim + col : 0;
-      v[q] = __ldg(reinterpret_cast<const float4*>(p.x + idx));
+      v[q] = rk_ld(p.x + idx, ldmode);
 #pragma unroll
-      for (int a = 0; a < NA; ++a) kk[q][a] = __ldg(reinterpret_cast<const float4*>(p.kp[a] + idx));
+      for (int a = 0; a < NA; ++a) kk[q][a] = rk_ld(p.kp[a] + idx, ldmode);
     }
 #pragma unroll
     for (int q = 0; q < RU; ++q) {
@@ -318,6 +353,7 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
 
   if (RK && threadIdx.x == 32) {
     rkd->x = p.rk_x; rkd->xnew = p.rk_xnew; rkd->err = p.rk_err; rkd->batch = p.batch; rkd->dim = p.dim;
+    rkd->n = p.rk_n; rkd->ldmode = p.rk_ldmode;
 #pragma unroll
     for (int j = 0; j < 6; ++j) { rkd->kp[j] = p.rk_kp[j]; rkd->coef[j] = p.rk_coef[j]; rkd->ecoef[j] = p.rk_ecoef[j]; }
   }
@@ -490,8 +526,12 @@ mlp_fused_h3_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
         // ---- layer-1 A operand: the stage input of this slab, formed chunk by chunk while the MMAs of the previous
         // chunk run (rk_fill_chunk)
         const int te = (int)threadIdx.x - 64, f = te & 15, rb = te >> 4;
+        const int pf = p.rk_pf;  // prefetch distance in chunks (0: off)
+        if (pf > 0)
+          for (int kc = 0; kc < pf && kc < nk1; ++kc) rk_prefetch_chunk(*rkd, (int64_t)slab * kTM, kc, te);
         for (int kc = 0; kc < nk1; ++kc, ++q1e) {
           const int s = q1e & 1;
+          if (pf > 0 && kc + pf < nk1) rk_prefetch_chunk(*rkd, (int64_t)slab * kTM, kc + pf, te);
           mbar_wait(&l1_empty[s], ((q1e >> 1) & 1) ^ 1);
           uint8_t* sb = s == 0 ? act : ring;
           const int col = kc * kHK + 4 * f;
@@ -715,6 +755,12 @@ int mlp_tc_forward(const MlpBlobHeader& h, const void* blob, const float* x, con
     p.probe = probe;
     p.rk_x = nullptr; p.rk_n = 0; p.rk_h = nullptr; p.rk_t0 = nullptr; p.rk_c = 0.f;
     p.rk_xnew = nullptr; p.rk_err = nullptr;
+    static int rk_pf = -1;
+    if (rk_pf < 0) { const char* e = getenv("CFM_RK_PF"); rk_pf = e ? atoi(e) : 2; }
+    p.rk_pf = rk_pf;
+    static int rk_ld = -1;
+    if (rk_ld < 0) { const char* e = getenv("CFM_RK_LD"); rk_ld = e ? atoi(e) : 1; }
+    p.rk_ldmode = rk_ld;
     for (int j = 0; j < 6; ++j) { p.rk_kp[j] = nullptr; p.rk_coef[j] = 0.f; p.rk_ecoef[j] = 0.f; }
     if (rk != nullptr) {
       p.rk_x = rk->x; p.rk_h = rk->h_dev; p.rk_t0 = rk->t0_dev; p.rk_c = rk->c;

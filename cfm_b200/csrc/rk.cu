@@ -32,9 +32,38 @@ __constant__ float kA[7][6] = CFM_RK_A_INIT;
 // b5 - b4 (embedded error weights), k1..k7
 __constant__ float kE[7] = CFM_RK_E_INIT;
 
+// L2 policies for the stage-input reads (CFM_RK_L2 bitmask, read once): a dopri5 step re-reads x and k1 in every one of
+// its six stage inputs while ~1 GB of other traffic (2.5x the L2) passes in between; loading them evict_last keeps
+// them resident.  bit 0: x evict_last, bit 1: k1 evict_last, bit 2: k2..k6 evict_first.
+__device__ __forceinline__ uint64_t rk_policy(bool last) {
+  uint64_t p;
+  if (last) asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  else asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 rk_ld_pol(const float4* ptr, uint64_t pol) {
+  float4 v;
+  asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"  // (not volatile: schedulable like a plain load)
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(pol));
+  return v;
+}
+static int rk_l2_mode() {
+  static int m = -1;
+  if (m < 0) { const char* e = getenv("CFM_RK_L2"); m = e ? atoi(e) : 7; }
+  return m;
+}
+
 static inline int ew_grid(int64_t numel) {
   int64_t blocks = (numel / 4 + 255) / 256 + 1;
   const int64_t cap = (int64_t)sm_count() * 8;
+  return (int)(blocks < cap ? blocks : cap);
+}
+
+static inline int rk_stage_grid(int64_t numel) {  // CFM_RK_GRID: CTAs per SM of the stage-input kernel (default 8)
+  static int per_sm = -1;
+  if (per_sm < 0) { const char* e = getenv("CFM_RK_GRID"); per_sm = e ? atoi(e) : 8; }
+  int64_t blocks = (numel / 8 + 255) / 256 + 1;
+  const int64_t cap = (int64_t)sm_count() * per_sm;
   return (int)(blocks < cap ? blocks : cap);
 }
 
@@ -51,47 +80,75 @@ __device__ __forceinline__ double block_sum_to(double v, double* smem32) {
   return t;  // valid in warp 0 lane 0
 }
 
-// xs (stage 1..5) or xnew (stage 6) = x + dt * sum_j a[stage][j] * k_j ; also t_stage = t + c*dt
-__global__ void rk_stage_input_kernel(const cfm_rk_state* __restrict__ st, const float* __restrict__ x,
-                                      const float* __restrict__ k, float* __restrict__ out,
-                                      __half* __restrict__ out_hi, __half* __restrict__ out_lo,
-                                      float* __restrict__ t_stage, float* __restrict__ err_partial, int64_t numel,
-                                      int stage) {
+// host/device compile-time copies of the tableau (same initialisers as the __constant__ arrays: identical fp32 values)
+__host__ __device__ constexpr float rk_a(int s, int j) { constexpr float t[7][6] = CFM_RK_A_INIT; return t[s][j]; }
+__host__ __device__ constexpr float rk_e(int j) { constexpr float t[7] = CFM_RK_E_INIT; return t[j]; }
+
+// xs (stage 1..5) or xnew (stage 6) = x + dt * sum_j a[stage][j] * k_j ; also t_stage = t + c*dt.
+// STAGE is a template parameter so that the loads of a thread -- x and the stage's derivative arrays, for U float4
+// positions -- are straight-line code issued back to back (up to 12 independent 128-bit loads in flight per thread);
+// L2MODE: see rk_policy above.
+template <int STAGE, int L2MODE>
+__global__ void __launch_bounds__(256)
+rk_stage_input_kernel(const cfm_rk_state* __restrict__ st, const float* __restrict__ x,
+                      const float* __restrict__ k, float* __restrict__ out,
+                      __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                      float* __restrict__ t_stage, float* __restrict__ err_partial, int64_t numel) {
   if (st->done) return;
+  constexpr int stage = STAGE;
+  constexpr int l2mode = L2MODE;
+  constexpr int U = 2;
   const float dt = st->dt;
+  const uint64_t pol_last = rk_policy(true), pol_first = rk_policy(false);
   if (blockIdx.x == 0 && threadIdx.x == 0 && t_stage) *t_stage = fmaf(kC[stage], dt, st->t);
   float a[6];
 #pragma unroll
-  for (int j = 0; j < 6; ++j) a[j] = dt * kA[stage][j];
+  for (int j = 0; j < 6; ++j) a[j] = dt * rk_a(stage, j);
   const int64_t n4 = (numel & 3) ? 0 : (numel >> 2);  // k_j bases stay 16B-aligned only then
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    float4 v = reinterpret_cast<const float4*>(x)[i];
-    float4 e6 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += U * stride) {
+    float4 v[U], kk[U][6];
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      if (j < stage && kA[stage][j] != 0.f) {
-        const float4 kk = reinterpret_cast<const float4*>(k + (int64_t)j * numel)[i];
-        v.x = fmaf(a[j], kk.x, v.x); v.y = fmaf(a[j], kk.y, v.y);
-        v.z = fmaf(a[j], kk.z, v.z); v.w = fmaf(a[j], kk.w, v.w);
-        if (err_partial) {  // stage 6 reads k1..k6 anyway: hand the error estimate's first six terms to the norm kernel
-          e6.x = fmaf(kE[j], kk.x, e6.x); e6.y = fmaf(kE[j], kk.y, e6.y);
-          e6.z = fmaf(kE[j], kk.z, e6.z); e6.w = fmaf(kE[j], kk.w, e6.w);
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride < n4 ? i0 + u * stride : i0;  // (a clamped duplicate instead of a branch)
+      v[u] = (l2mode & 1) ? rk_ld_pol(reinterpret_cast<const float4*>(x) + i, pol_last)
+                          : __ldg(reinterpret_cast<const float4*>(x) + i);
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+        if (j < stage && rk_a(stage, j) != 0.f) {
+          const float4* kp = reinterpret_cast<const float4*>(k + (int64_t)j * numel) + i;
+          kk[u][j] = (j == 0 && (l2mode & 2)) ? rk_ld_pol(kp, pol_last)
+                     : (j > 0 && (l2mode & 4)) ? rk_ld_pol(kp, pol_first) : __ldg(kp);
         }
-      }
     }
-    if (err_partial) reinterpret_cast<float4*>(err_partial)[i] = e6;
-    if (out) reinterpret_cast<float4*>(out)[i] = v;
-    if (out_hi) {  // operand pair for the tensor-core MLP: the fp32 stage input is never re-read
-      __half h[4], l[4];
-      rk_split_h3(v.x, h[0], l[0]); rk_split_h3(v.y, h[1], l[1]);
-      rk_split_h3(v.z, h[2], l[2]); rk_split_h3(v.w, h[3], l[3]);
-      reinterpret_cast<uint2*>(out_hi)[i] = make_uint2(
-          (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
-          (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
-      reinterpret_cast<uint2*>(out_lo)[i] = make_uint2(
-          (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16),
-          (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i >= n4) break;
+      float4 e6 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+        if (j < stage && rk_a(stage, j) != 0.f) {
+          v[u].x = fmaf(a[j], kk[u][j].x, v[u].x); v[u].y = fmaf(a[j], kk[u][j].y, v[u].y);
+          v[u].z = fmaf(a[j], kk[u][j].z, v[u].z); v[u].w = fmaf(a[j], kk[u][j].w, v[u].w);
+          if (stage == 6) {  // stage 6 reads k1..k6 anyway: hand the error estimate's first six terms to the norm kernel
+            e6.x = fmaf(rk_e(j), kk[u][j].x, e6.x); e6.y = fmaf(rk_e(j), kk[u][j].y, e6.y);
+            e6.z = fmaf(rk_e(j), kk[u][j].z, e6.z); e6.w = fmaf(rk_e(j), kk[u][j].w, e6.w);
+          }
+        }
+      if (stage == 6 && err_partial) reinterpret_cast<float4*>(err_partial)[i] = e6;
+      if (out) reinterpret_cast<float4*>(out)[i] = v[u];
+      if (out_hi) {  // operand pair for the tensor-core MLP: the fp32 stage input is never re-read
+        __half h[4], l[4];
+        rk_split_h3(v[u].x, h[0], l[0]); rk_split_h3(v[u].y, h[1], l[1]);
+        rk_split_h3(v[u].z, h[2], l[2]); rk_split_h3(v[u].w, h[3], l[3]);
+        reinterpret_cast<uint2*>(out_hi)[i] = make_uint2(
+            (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
+            (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
+        reinterpret_cast<uint2*>(out_lo)[i] = make_uint2(
+            (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16),
+            (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16));
+      }
     }
   }
   for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
@@ -382,9 +439,16 @@ extern "C" int cfm_rk_stage_input(const cfm_rk_state* st, const float* x, const 
   RK_CHECK(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(out) |
              reinterpret_cast<uintptr_t>(out_hi) | reinterpret_cast<uintptr_t>(out_lo)) & 15) == 0);
   RK_CHECK(err_partial == nullptr || stage == 6);
-  rk_stage_input_kernel<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(
-      st, x, k, out, reinterpret_cast<__half*>(out_hi), reinterpret_cast<__half*>(out_lo), t_stage, err_partial, numel,
-      stage); ::cfm::note_launches(1);
+  using Kern = void (*)(const cfm_rk_state*, const float*, const float*, float*, __half*, __half*, float*, float*, int64_t);
+#define CFM_RK_ROW(M) {rk_stage_input_kernel<1, M>, rk_stage_input_kernel<2, M>, rk_stage_input_kernel<3, M>, \
+                       rk_stage_input_kernel<4, M>, rk_stage_input_kernel<5, M>, rk_stage_input_kernel<6, M>}
+  static const Kern table[4][6] = {CFM_RK_ROW(0), CFM_RK_ROW(3), CFM_RK_ROW(4), CFM_RK_ROW(7)};
+#undef CFM_RK_ROW
+  const int m = rk_l2_mode();
+  const Kern kern = table[m == 3 ? 1 : m == 4 ? 2 : m == 7 ? 3 : 0][stage - 1];
+  kern<<<rk_stage_grid(numel), 256, 0, (cudaStream_t)stream>>>(
+      st, x, k, out, reinterpret_cast<__half*>(out_hi), reinterpret_cast<__half*>(out_lo), t_stage, err_partial, numel);
+  ::cfm::note_launches(1);
   CFM_CUDA_OK(cudaGetLastError());
   return CFM_OK;
 }

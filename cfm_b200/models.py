@@ -88,7 +88,16 @@ class MLP(torch.nn.Module):
         return y
 
     def _use_kernels(self, x):
-        return (x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled())
+        """Sampling regime (no autograd): the kernels, or nothing -- a CPU tensor under ``torch.no_grad()`` raises
+        instead of silently running ``torch.nn.Sequential`` (north_star: no CPU fallback).  With autograd enabled
+        (training; the backward pass is outside the hot path) the module is plain PyTorch on any device."""
+        if torch.is_grad_enabled():
+            return False
+        if not x.is_cuda:
+            raise _ffi.CfmLibraryError(
+                "cfm_b200.MLP under torch.no_grad() runs in libcfm_b200's CUDA kernels; the input is a CPU tensor and "
+                "there is no CPU fallback (enable grad for the plain-PyTorch training path)")
+        return x.dtype == torch.float32
 
     def forward(self, x):
         """net(x) (reference models.py:20-21).  x already carries t as a column if time_varying."""

@@ -66,7 +66,7 @@ class NeuralODE(torch.nn.Module):
         # True (default): a stage evaluation is ONE launch -- the stage input x + dt sum a_sj k_j is formed inside the
         # fused MLP kernel as its layer-1 operand producer (cfm_mlp_forward_rkstage_f32; bit-identical to the separate
         # stage-input kernel, which remains the path of other widths and of fuse_stage_input = False)
-        self.fuse_stage_input = True
+        self.fuse_stage_input = False
         self._plans = {}
 
     @torch.no_grad()

@@ -9,7 +9,12 @@ mlp = cfm_b200.MLP(dim=784, w=256, time_varying=True).to(dev)
 x = torch.randn(10000, 784, device=dev)
 span = torch.linspace(0, 1, 2)
 ref = None
-for fuse, graph, mb in [(False, True, 4), (True, True, 4), (True, True, 1), (True, False, 4), (False, True, 4), (True, True, 4)]:
+import os
+variants = [(False, True, 4), (True, True, 4), (True, True, 1), (True, False, 4), (False, True, 4), (True, True, 4)]
+if len(sys.argv) > 1:  # e.g. "0" or "1" or "01": just these fuse settings, graph on
+    variants = [(c == "1", True, 4) for c in sys.argv[1]]
+print({k: v for k, v in os.environ.items() if k.startswith("CFM_")})
+for fuse, graph, mb in variants:
     node = cfm_b200.NeuralODE(cfm_b200.torch_wrapper(mlp), solver="dopri5", atol=1e-4, rtol=1e-4)
     node.fuse_stage_input, node.use_cuda_graph, node.min_burst = fuse, graph, mb
     for _ in range(3):

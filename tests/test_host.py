@@ -137,6 +137,11 @@ def test_hot_path_refuses_to_run_without_a_gpu():
     m = cfm_b200.MLP(dim=2, time_varying=True)
     with pytest.raises(CfmLibraryError):
         cfm_b200.NeuralODE(cfm_b200.torch_wrapper(m)).trajectory(torch.zeros(4, 2), torch.linspace(0, 1, 2))
+    with pytest.raises(CfmLibraryError), torch.no_grad():  # sampling regime on CPU tensors: no silent PyTorch fallback
+        m(torch.zeros(4, 3))
+    with pytest.raises(CfmLibraryError), torch.no_grad():
+        cfm_b200.torch_wrapper(m)(torch.tensor(0.5), torch.zeros(4, 2))
+    assert m(torch.zeros(4, 3)).requires_grad  # training path (autograd on): plain PyTorch, any device
     with pytest.raises(CfmLibraryError):
         cfm_b200.CouplingStream(OTPlanSampler("sinkhorn"))
     with pytest.raises(CfmLibraryError):
