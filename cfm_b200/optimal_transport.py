@@ -134,7 +134,7 @@ class OTPlanSampler:
         self.warn = warn
         self.num_iter_max = int(num_iter_max)
         self.stop_thr = float(stop_thr)
-        if precision not in ("auto", "fp32", "fp64", "fp32-generic", "fp64-mixed"):
+        if precision not in ("auto", "fp32", "fp64", "fp32-generic", "fp64-mixed", "fp64-mixed-unscreened"):
             raise ValueError(f"Unknown precision: {precision}")
         self.precision = precision
         self.stall_tol = float(stall_tol)
@@ -238,7 +238,8 @@ class OTPlanSampler:
         # the status word and the error are per call: a deferred report may read them after later solves
         cp.status = torch.zeros(4, dtype=torch.int32, device=dev)
         cp.err = torch.zeros(1, dtype=torch.float64, device=dev)
-        prec = {"auto": -1, "fp32": 0, "fp64": 1, "fp32-generic": 2, "fp64-mixed": 3}[self.precision]
+        prec = {"auto": -1, "fp32": 0, "fp64": 1, "fp32-generic": 2, "fp64-mixed": 3,
+                "fp64-mixed-unscreened": 4}[self.precision]
         with torch.cuda.device(dev):
             _ffi.check(L.cfm_sinkhorn_log_f32(
                 _ffi.ptr(Mbuf), n0, n1, Mbuf.stride(0), float(reg), _ffi.ptr(cmax), int(bool(normalize)),

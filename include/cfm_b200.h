@@ -74,8 +74,10 @@ int cfm_tc_debug_buffer(unsigned long long* buf);
  * precise: 0 = fp32 exponent arithmetic (|M/reg| <~ 64), 1 = float64 potentials and
  * IEEE fp32 division for -M/reg exactly as NumPy forms it, -1 = choose on device from
  * *cost_max / reg, 2 = fp32 arithmetic forced onto the generic (L2-reuse) kernel, 3 = float64
- * potentials and exponent arguments with fp32 exponentials (terms good to ~1e-7; five times fewer
- * float64-pipe instructions than mode 1).
+ * potentials and exponent arguments with fp32 exponentials (terms good to ~1e-7).  In mode 3 (and in -1 when it
+ * resolves to it) every term of a log-sum-exp is first screened in fp32 against (running maximum - 32): terms
+ * more than ~30 units below the maximum (< 1e-13 of it) skip the float64 path; 4 = mode 3 without that
+ * screening (cross-checks).
  * Outputs: log_u (n0), log_v (n1) float64 natural-log potentials with
  *   plan_ij = exp(-M_ij/reg + log_u_i + log_v_j);
  * stall_tol: 0 = POT's stopping rule only.  > 0 additionally stops at a check when the

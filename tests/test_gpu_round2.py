@@ -451,3 +451,62 @@ def test_rkstage_single_evaluation_against_the_float64_oracle():
     xs2 = (x.double() + 0.125 * (3 / 40 * k[0].double() + 9 / 40 * k[1].double())).float()
     ref2 = f64(float(np.float32(0.25) + np.float32(0.3) * np.float32(0.125)), xs2)
     assert (kd[2].cpu().double() - ref2).abs().max() <= 1e-5 * ref2.abs().max()
+
+
+# ------------------------------------------------- float64-potential Sinkhorn with fp32 screening (BASELINE config 4)
+def _sk(M, reg, precision, iters, normalize=False):
+    """Solve on a given cost matrix (the oracle's own M) through OTPlanSampler's solver stage."""
+    s = OTPlanSampler("sinkhorn", reg=reg, precision=precision, stall_tol=0.0, num_iter_max=iters, stop_thr=0.0, warn=False)
+    n0, n1 = M.shape
+    ld = (n1 + 3) // 4 * 4
+    buf = torch.zeros((n0, ld), dtype=torch.float32, device=DEV)
+    buf[:, :n1] = M.to(DEV)
+    cmax = M.max().reshape(1).float().to(DEV)
+    cp = s._solve_sinkhorn(buf, cmax, n0, n1, reg, normalize)
+    st = cp.status.cpu().tolist()
+    return cp, cp.log_u.cpu().numpy(), cp.log_v.cpu().numpy(), st, float(cp.err.item())
+
+
+@pytest.mark.parametrize("n0,n1,d,reg,normalize", [(2048, 2048, 512, 0.1, False), (1000, 1500, 64, 0.01, False),
+                                                   (777, 515, 32, 0.002, True), (4096, 4096, 512, 0.1, False)])
+def test_screened_mixed_sinkhorn_equals_the_unscreened_and_float64_solvers(n0, n1, d, reg, normalize):
+    """The fp32 screening of negligible log-sum-exp terms (mode 3 / auto in the |M/reg| >> 64 regime) changes which
+    terms take the float64 path, not the result: potentials within 1e-6 of the unscreened mixed solver (4e-6 of the
+    all-float64 solver) after 1, 7 and 60 iterations -- aligned and ragged shapes, rectangular, normalised cost."""
+    g = torch.Generator().manual_seed(n0 + n1)
+    x0, x1 = torch.randn(n0, d, generator=g), torch.randn(n1, d, generator=g) + 0.1
+    M = oc.cost_matrix(x0, x1)
+    scale = float(M.max()) if normalize else 1.0
+    assert float(M.max()) / scale / reg > 200
+    for iters in (1, 7, 60):
+        _, lu, lv, st, _ = _sk(M, reg, "fp64-mixed", iters, normalize)
+        _, lu0, lv0, st0, _ = _sk(M, reg, "fp64-mixed-unscreened", iters, normalize)
+        _, lu1, lv1, st1, _ = _sk(M, reg, "fp64", iters, normalize)
+        assert st[2] == 2 and st0[2] == 2 and st1[2] == 1
+        assert np.abs(lu - lu0).max() < 1e-6 and np.abs(lv - lv0).max() < 1e-6, iters
+        # against all-float64 arithmetic: the fp32 exponentials of mixed mode (1e-7 per term) accumulate over iterations
+        assert np.abs(lu - lu1).max() < 4e-6 and np.abs(lv - lv1).max() < 4e-6, iters
+    _, lua, lva, sta, _ = _sk(M, reg, "auto", 60, normalize)
+    assert sta[2] == 2 and np.array_equal(lua, lu) and np.array_equal(lva, lv)  # auto resolves to the screened path
+
+
+def test_screened_mixed_sinkhorn_wide_row_offsets_and_nan():
+    """Row norms spread over three decades put large offsets into u as well as v (both potentials ~1e4, their
+    cancellation with -M/reg is what the float64 path is for): the screening margin must still hold.  A NaN cost is
+    never screened out: it reaches the potentials as in the unscreened solver."""
+    g = torch.Generator().manual_seed(5)
+    n, d = 512, 16
+    x0 = torch.randn(n, d, generator=g) * torch.logspace(-1, 1.3, n)[:, None]
+    x1 = torch.randn(n, d, generator=g) * torch.logspace(1.3, -1, n)[:, None]
+    M = oc.cost_matrix(x0, x1)
+    assert float(M.max()) / 0.5 > 5e3
+    for iters in (1, 25):
+        _, lu, lv, st, _ = _sk(M, 0.5, "fp64-mixed", iters)
+        _, lu1, lv1, _, _ = _sk(M, 0.5, "fp64", iters)
+        assert st[2] == 2
+        tol = 1e-9 * float(M.max()) / 0.5 + 1e-6  # float64 cancellation floor of potentials this large
+        assert np.abs(lu - lu1).max() < tol and np.abs(lv - lv1).max() < tol, iters
+    Mn = M.clone()
+    Mn[3, 7] = float("nan")
+    _, lu, lv, st, err = _sk(Mn, 0.5, "fp64-mixed", 5)
+    assert np.isnan(lu[3]) and np.isnan(lv[7])
