@@ -476,23 +476,28 @@ __device__ void sinkhorn_run(const SkParams& p, unsigned char* smem_raw) {
 // assumed: if the potentials moved a lot the thresholds merely drop and more terms take the exact path.
 // Per iteration: row pass over the CTA's slab -> grid barrier (global min of du) -> column pass -> barrier ->
 // combine (v_new, min of dv, marginal error) -> barrier.
-template <bool VEC>
-__device__ __forceinline__ double row_lse_seeded(const float* __restrict__ row, const double* v_s,
-                                                 const float* vh_s, int n1, int ng, const Xf<true>& xf, float nr,
-                                                 float thr, int lane, bool& empty) {
-  constexpr int U = 4;
+// candidates of the float4 groups [g_begin, g_end) of one row -> warp-reduced (maximum, sum relative to it)
+template <bool VEC, int U, bool L1>
+__device__ __forceinline__ void row_range_seeded(const float* __restrict__ row, const double* v_s, const float* vh_s,
+                                                 int n1, int g_begin, int g_end, const Xf<true>& xf, float nr, float thr,
+                                                 int lane, double& wm, double& ws) {
   double m = Tr<true>::init(), s = 0.0;
-  for (int g0 = 0; g0 < ng; g0 += 32 * U) {
+  for (int g0 = g_begin; g0 < g_end; g0 += 32 * U) {
     unsigned gm = 0;  // bit q: float4 group q of this lane holds a candidate
+    float4 c[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q) {  // all loads of the block first: U independent 128-bit loads in flight per lane
+      const int g = g0 + q * 32 + lane;
+      if (g < g_end) c[q] = (VEC && L1) ? __ldg(reinterpret_cast<const float4*>(row + g * 4)) : load_cost4<VEC>(row, g * 4, n1);
+    }
 #pragma unroll
     for (int q = 0; q < U; ++q) {
       const int g = g0 + q * 32 + lane;
-      if (g < ng) {
-        const float4 c = load_cost4<VEC>(row, g * 4, n1);
+      if (g < g_end) {
         const float4 vh = *reinterpret_cast<const float4*>(vh_s + g * 4);
         // (NaN fails `<=`: a NaN cost or potential is a candidate, never dropped)
-        const bool le = (fmaf(c.x, nr, vh.x) <= thr) & (fmaf(c.y, nr, vh.y) <= thr) & (fmaf(c.z, nr, vh.z) <= thr) &
-                        (fmaf(c.w, nr, vh.w) <= thr);
+        const bool le = (fmaf(c[q].x, nr, vh.x) <= thr) & (fmaf(c[q].y, nr, vh.y) <= thr) &
+                        (fmaf(c[q].z, nr, vh.z) <= thr) & (fmaf(c[q].w, nr, vh.w) <= thr);
         gm |= (le ? 0u : 1u) << q;
       }
     }
@@ -507,8 +512,16 @@ __device__ __forceinline__ double row_lse_seeded(const float* __restrict__ row, 
       }
     }
   }
-  const double wm = warp_max(m);
-  const double ws = warp_sum(s * expd<true>(m, wm));
+  wm = warp_max(m);
+  ws = warp_sum(s * expd<true>(m, wm));
+}
+
+template <bool VEC>
+__device__ __forceinline__ double row_lse_seeded(const float* __restrict__ row, const double* v_s,
+                                                 const float* vh_s, int n1, int ng, const Xf<true>& xf, float nr,
+                                                 float thr, int lane, bool& empty) {
+  double wm, ws;
+  row_range_seeded<VEC, 4, false>(row, v_s, vh_s, n1, 0, ng, xf, nr, thr, lane, wm, ws);
   empty = !(ws > 0.0);  // (cannot happen with a valid bound; the caller then repeats the row unseeded)
   return lse_fin(wm, ws);
 }
@@ -679,6 +692,112 @@ __device__ void sinkhorn_run_seeded(const SkParams& p, unsigned char* smem_raw) 
     }
   };
 
+
+  // Fused sweep (iterations >= 1): per chunk of 8 rows the row LSEs (two warps per row, half a row each) and, with the
+  // fresh u, the column candidates of the same rows -- the chunk (8 x 16 KB at n1 = 4096) is still in L1, so M crosses
+  // the L2 -> SM path once per iteration and no grid barrier separates the two phases.  The column thresholds need the
+  // global minimum of this iteration's u changes, which is not known yet: an ASSUMED value is used (the previous
+  // iteration's minimum - 8) and verified after the barrier; the caller repeats the column pass in the rare case it
+  // was too optimistic.
+  __shared__ double half_m[2][8], half_s[2][8];
+  auto fused_phase = [&](float dv_min, float du_assumed) {
+    double cm[KG][4], cs[KG][4];
+    float cthr[KG][4];
+#pragma unroll
+    for (int k = 0; k < KG; ++k)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        cm[k][c] = Tr<true>::init(); cs[k][c] = 0.0;
+        const int col = (tid + kSkThreads * k) * 4 + c;
+        cthr[k][c] = col < n1 ? __double2float_rd(logb - v_s[col] + (double)du_assumed) - kScreenGap : kBig;
+      }
+    const int ngh = ((ng + 1) / 2 + 31) / 32 * 32;  // float4 groups of the first half-row
+    const int rr = warp & 7, half = warp >> 3;
+    float dmin = kBig;
+    for (int r0 = r_begin; r0 < r_end; r0 += 8) {
+      const int R = min(8, r_end - r0);
+      if (rr < R) {
+        const float* row = p.M + (int64_t)(r0 + rr) * p.ldm;
+        const float thr = __double2float_rd(loga - u_work[r0 + rr] + (double)dv_min) - kScreenGap;
+        double wm, ws;
+        row_range_seeded<VEC, 8, true>(row, v_s, vh_s, n1, half ? ngh : 0, half ? ng : min(ngh, ng), xf, nr, thr, lane, wm, ws);
+        if (lane == 0) { half_m[half][rr] = wm; half_s[half][rr] = ws; }
+      }
+      __syncthreads();
+      if (warp < R) {  // warp w finishes row r0 + w
+        const double m0 = half_m[0][warp], m1 = half_m[1][warp];
+        const double mm = vmax(m0, m1);
+        const double ss = half_s[0][warp] * expd<true>(m0, mm) + half_s[1][warp] * expd<true>(m1, mm);
+        double lse = lse_fin(mm, ss);
+        const float* row = p.M + (int64_t)(r0 + warp) * p.ldm;
+        if (!(ss > 0.0)) lse = row_lse_screened<VEC>(row, v_s, vh_s, n1, ng, xf, nr, lane);  // (warp-uniform; never with a valid bound)
+        const double uval = loga - lse;
+        if (lane == 0) {
+          dmin = fminf(dmin, __double2float_rd(uval - u_work[r0 + warp]));
+          u_work[r0 + warp] = uval;
+          p.log_u[r0 + warp] = uval;
+          u_chunk[warp] = uval; uh_chunk[warp] = (float)uval;
+        }
+      } else if (warp < 8 && lane == 0) {
+        u_chunk[warp] = 0.0; uh_chunk[warp] = 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < KG; ++k) {
+        const int g = tid + kSkThreads * k;
+        const bool gv = g < ng;
+        float4 c[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (gv && q < R) {
+            c[q] = VEC ? __ldg(reinterpret_cast<const float4*>(p.M + (int64_t)(r0 + q) * p.ldm + g * 4))
+                       : load_cost4<VEC>(p.M + (int64_t)(r0 + q) * p.ldm, g * 4, n1);
+          } else {
+            const float inf = __int_as_float(0x7f800000);
+            c[q] = make_float4(inf, inf, inf, inf);
+          }
+        }
+        float uh[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) uh[q] = uh_chunk[q];
+        unsigned hm = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const bool le = (fmaf(c[q].x, nr, uh[q]) <= cthr[k][0]) & (fmaf(c[q].y, nr, uh[q]) <= cthr[k][1]) &
+                          (fmaf(c[q].z, nr, uh[q]) <= cthr[k][2]) & (fmaf(c[q].w, nr, uh[q]) <= cthr[k][3]);
+          hm |= (le ? 0u : 1u) << q;
+        }
+        while (__any_sync(0xffffffffu, hm != 0u)) {
+          if (hm != 0u) {
+            const int e = __ffs((int)hm) - 1;
+            hm &= hm - 1u;
+            const float4 c01 = (e & 1) ? ((e & 2) ? c[3] : c[1]) : ((e & 2) ? c[2] : c[0]);
+            const float4 c45 = (e & 1) ? ((e & 2) ? c[7] : c[5]) : ((e & 2) ? c[6] : c[4]);
+            const float4 ce = (e & 4) ? c45 : c01;
+            const float ue = uh_chunk[e];
+            const double ud = u_chunk[e];
+            if (!(fmaf(ce.x, nr, ue) <= cthr[k][0])) lse_take(xf(ce.x, ud), cm[k][0], cs[k][0]);
+            if (!(fmaf(ce.y, nr, ue) <= cthr[k][1])) lse_take(xf(ce.y, ud), cm[k][1], cs[k][1]);
+            if (!(fmaf(ce.z, nr, ue) <= cthr[k][2])) lse_take(xf(ce.z, ud), cm[k][2], cs[k][2]);
+            if (!(fmaf(ce.w, nr, ue) <= cthr[k][3])) lse_take(xf(ce.w, ud), cm[k][3], cs[k][3]);
+          }
+        }
+      }
+      // (no third barrier: u_chunk / half_* are rewritten only behind the next chunk's first barrier)
+    }
+#pragma unroll
+    for (int k = 0; k < KG; ++k) {
+      const int g = tid + kSkThreads * k;
+      if (g >= ng) continue;
+      double* pm = part_m + (int64_t)b * n1p + g * 4;
+      double* ps = part_s + (int64_t)b * n1p + g * 4;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { pm[c] = cm[k][c]; ps[c] = cs[k][c]; }
+    }
+    dmin = block_min_f(lane == 0 ? dmin : kBig, redf, tid);
+    if (tid == 0) dmin_u[b] = dmin;
+  };
+
   // combine the per-CTA column partials of a slice of columns -> v_new, marginal error, min of (v_new - v_cur)
   auto combine = [&](const double* v_cur, double* v_new, bool have_cur, double* err_slot) {
     const int cpc = (n1 + nblk - 1) / nblk;
@@ -751,22 +870,52 @@ __device__ void sinkhorn_run_seeded(const SkParams& p, unsigned char* smem_raw) 
   int cur = 0, iters = 0;
   bool converged = false;
   double err = 1.0, prev_check_err = -1.0;
+  float du_prev = 0.f;  // global minimum of the u changes of the previous iteration
+  // CFM_SK_TL=1: %globaltimer marks of iteration 50 for the first and the last CTA (scripts/c4_timeline.py)
+  unsigned long long* tl = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(p.err_ring) + 4608) + (b == 0 ? 0 : 16);
+  const bool tl_on = p.timeline && (b == 0 || b == nblk - 1) && tid == 0;
+#define SK_TL(slot) do { if (tl_on && it == 50) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tl[slot] = t_; } } while (0)
   for (int it = 0; it < p.max_iters; ++it) {
     const bool last = (it == p.max_iters - 1);
     const bool check = (it % p.check_every) == 0;
     const bool do_col = !last || check;
+    SK_TL(0);
     stage_v(v_work[cur]);
+    SK_TL(1);
     const float dv_min = it > 0 ? global_min(dmin_v) : 0.f;
-    row_phase(it > 0, dv_min);
-    iters = it + 1;
-    if (!do_col) break;
-    grid.sync();
-    const float du_min = global_min(dmin_u);
-    col_phase(true, true, du_min);
-    grid.sync();
+    SK_TL(2);
+    const bool fused = it > 0 && do_col && p.screen_fused;
+    if (!fused) {
+      row_phase(it > 0, dv_min);
+      SK_TL(3);
+      iters = it + 1;
+      if (!do_col) break;
+      grid.sync();
+      SK_TL(4);
+      du_prev = global_min(dmin_u);
+      col_phase(true, true, du_prev);
+      SK_TL(5);
+      grid.sync();
+      SK_TL(6);
+    } else {
+      const float du_assumed = du_prev - 8.f;
+      fused_phase(dv_min, du_assumed);
+      SK_TL(5);
+      iters = it + 1;
+      grid.sync();
+      SK_TL(6);
+      du_prev = global_min(dmin_u);   // the true minimum: every CTA reads the same slots and takes the same branch
+      if (!(du_prev >= du_assumed)) {  // the assumption was too optimistic (or NaN): column pass again, exact bound
+        col_phase(true, true, du_prev);
+        grid.sync();
+      }
+    }
+    SK_TL(7);
     if (b == 0 && tid == 0) p.err_ring[(it + 2) & 3] = 0.0;
     combine(v_work[cur], v_work[cur ^ 1], true, &p.err_ring[it & 3]);
+    SK_TL(8);
     grid.sync();
+    SK_TL(9);
     if (check) {
       err = sqrt(__ldcg(&p.err_ring[it & 3]));
       if (err < p.stop_thr) { converged = true; break; }
@@ -778,6 +927,7 @@ __device__ void sinkhorn_run_seeded(const SkParams& p, unsigned char* smem_raw) 
     if (last) break;
     cur ^= 1;
   }
+#undef SK_TL
 
   for (int j = b * kSkThreads + tid; j < n1; j += nblk * kSkThreads) p.log_v[j] = __ldcg(v_work[cur] + j);
   if (b == 0 && tid == 0) {
@@ -944,6 +1094,12 @@ extern "C" int cfm_sinkhorn_log_f32(const float* M, int n0, int n1, int64_t ldm,
   static int screen = -1;
   if (screen < 0) { const char* e = getenv("CFM_SK_SCREEN"); screen = e ? atoi(e) : 1; }
   p.screen = screen_off ? 0 : screen;
+  static int sfused = -1;
+  if (sfused < 0) { const char* e = getenv("CFM_SK_FUSED"); sfused = e ? atoi(e) : 1; }
+  p.screen_fused = sfused;
+  static int tl = -1;
+  if (tl < 0) { const char* e = getenv("CFM_SK_TL"); tl = e ? atoi(e) : 0; }
+  p.timeline = tl;
   const int ng = p.n1p / 4;
   const int kg_need = (ng + kSkThreads - 1) / kSkThreads;
   if (p.vec) {
