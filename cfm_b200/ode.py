@@ -345,6 +345,12 @@ class NeuralODE(torch.nn.Module):
             # many steps can be enqueued without looking; a step enqueued after t_end is a no-op on the
             # device (done flag), so the bound only has to be safe, not tight.
             burst = max(1 if lock else self.min_burst, min(self.max_burst, n_span - int(cur.ckpt)))
+            if not lock and steps == 0 and P.get("last_steps"):
+                # the previous trajectory of this plan (same model, same span, same batch shape) is the best predictor
+                # of the step count: enqueue exactly that many, then look; a wrong guess costs one more round trip
+                burst = max(n_span - 1, min(self.max_burst, P["last_steps"]))
+            elif not lock and steps > 0 and P.get("last_steps"):
+                burst = max(1, min(burst, 2))
             for _ in range(burst):
                 if P["graph"] is not None and not lock:
                     P["graph"].replay()
@@ -358,6 +364,7 @@ class NeuralODE(torch.nn.Module):
                 break
         else:
             raise RuntimeError("dopri5: step budget exhausted")
+        P["last_steps"] = int(cur.accepted) + int(cur.rejected)
         self.stats = {"nfe": cur.nfe, "accepted": cur.accepted, "rejected": cur.rejected,
                       "t": cur.t, "last_ratio": cur.ratio, "graph": P["graph"] is not None and not lock,
                       "lockstep": lock}
