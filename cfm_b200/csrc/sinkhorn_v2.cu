@@ -528,6 +528,25 @@ __global__ void __launch_bounds__(NT, 512 / NT) sinkhorn_v2_kernel(const SkParam
             for (int q = 0; q < 4; ++q) acc += ss[q] * ex2f(mm[q] - bm);
             s = acc; m = bm;
           }
+        } else if (!(p.dbg_flags & 4) && nblk <= 152) {
+          // every lane loads ALL its <= 19 (max, sum) pairs before it reduces: ONE L2 round trip per column instead of
+          // three dependent ones (the combine sits between the two grid barriers: its latency is fixed cost per iteration)
+          float mm[19], ss[19];
+#pragma unroll
+          for (int q = 0; q < 19; ++q) {
+            const int c = sub + q * 8;
+            if (c < nblk) {
+              mm[q] = __ldcg(part_m + (int64_t)c * n1p + j);
+              ss[q] = __ldcg(part_s + (int64_t)c * n1p + j);
+            } else { mm[q] = -1.0e30f; ss[q] = 0.f; }
+          }
+          float bm = m;
+#pragma unroll
+          for (int q = 0; q < 19; ++q) bm = fmaxf(bm, mm[q]);
+          float acc = 0.f;
+#pragma unroll
+          for (int q = 0; q < 19; ++q) acc += ss[q] * ex2f(mm[q] - bm);
+          s = acc; m = bm;
         } else
         for (int c0 = sub; c0 < nblk; c0 += 64) {  // 8 independent (max, sum) pairs in flight per lane
           float mm[8], ss[8];
@@ -756,8 +775,10 @@ int sinkhorn_v2_launch(SkParams& p, cudaStream_t s) {
   if (l2frac < -1.f) { const char* e = getenv("CFM_SK_L2"); l2frac = e ? (float)atof(e) : 0.15f; }  // measured: 0.1-0.2 best (4.68 ms vs 4.92 ms at 0)
   // only worth it when M does not fit in L2 anyway (it is then fully resident by itself)
   p.l2_resident_frac = ((size_t)p.n0 * p.n1 * 4 > (size_t)100 << 20) ? l2frac : 0.f;
-  static int dbg = -1;  // CFM_SK_DBG: A/B switches (bit0: 4-wide combine loads, bit1: marginal error every iteration)
-  if (dbg < 0) { const char* e = getenv("CFM_SK_DBG"); dbg = e ? atoi(e) : 1; }  // same-box A/B: 4-wide loads 45.6 us/iter, 8-wide 45.9, error every iteration +0.9
+  static int dbg = -1;  // CFM_SK_DBG: A/B switches (bit0: 4-wide combine loop, bit2: 8-wide loop, bit1: marginal error every iteration)
+  // same-box A/B at C2 (solve, ms): 4-wide loop (bit 0) 4.469, 8-wide loop (bit 2) 4.468, all <= 19 partials of a lane in one
+  // round trip (0, default) 4.448 -- the combine's loads are ~0.2 us of the 10 us between two sweeps; error every iteration +0.9 us
+  if (dbg < 0) { const char* e = getenv("CFM_SK_DBG"); dbg = e ? atoi(e) : 0; }
   p.dbg_flags = dbg;
   static int pf = -1;  // CFM_SK_PF: chunks (of R rows) per CTA prefetched into L2 at the end of every sweep
   // measured on B200 at C2 (same box, 10 steps each): 0 -> 4.53 ms, 3 -> 4.60, 6 -> 4.76, 10 -> 5.16, 14 -> 5.61:
