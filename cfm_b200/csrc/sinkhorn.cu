@@ -506,9 +506,11 @@ __device__ __forceinline__ void row_range_seeded(const float* __restrict__ row, 
         const int q = __ffs((int)gm) - 1;
         gm &= gm - 1u;
         const int col0 = (g0 + q * 32 + lane) * 4;
+        const float4 cq = (VEC && L1) ? __ldg(reinterpret_cast<const float4*>(row + col0)) : load_cost4<VEC>(row, col0, n1);
+        const float ce[4] = {cq.x, cq.y, cq.z, cq.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (col0 + e < n1) lse_take(xf(__ldg(row + col0 + e), v_s[col0 + e]), m, s);
+        for (int e = 0; e < 4; ++e)  // only the elements of the group that are candidates themselves
+          if (col0 + e < n1 && !(fmaf(ce[e], nr, vh_s[col0 + e]) <= thr)) lse_take(xf(ce[e], v_s[col0 + e]), m, s);
       }
     }
   }
