@@ -716,8 +716,12 @@ __device__ void sinkhorn_run_seeded(const SkParams& p, unsigned char* smem_raw) 
     const int ngh = ((ng + 1) / 2 + 31) / 32 * 32;  // float4 groups of the first half-row
     const int rr = warp & 7, half = warp >> 3;
     float dmin = kBig;
+    unsigned long long* ctl = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(p.err_ring) + 4608) + (b == 0 ? 0 : 16);
+    const bool ctl_on = p.timeline == 2 && (b == 0 || b == nblk - 1) && (tid == 0 || tid == 511);
+#define SK_TLC(slot) do { if (ctl_on && r0 == r_begin + 8) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); ctl[(slot) + (tid == 0 ? 0 : 5)] = t_; } } while (0)
     for (int r0 = r_begin; r0 < r_end; r0 += 8) {
       const int R = min(8, r_end - r0);
+      SK_TLC(0);
       if (rr < R) {
         const float* row = p.M + (int64_t)(r0 + rr) * p.ldm;
         const float thr = __double2float_rd(loga - u_work[r0 + rr] + (double)dv_min) - kScreenGap;
@@ -725,7 +729,9 @@ __device__ void sinkhorn_run_seeded(const SkParams& p, unsigned char* smem_raw) 
         row_range_seeded<VEC, 8, true>(row, v_s, vh_s, n1, half ? ngh : 0, half ? ng : min(ngh, ng), xf, nr, thr, lane, wm, ws);
         if (lane == 0) { half_m[half][rr] = wm; half_s[half][rr] = ws; }
       }
+      SK_TLC(1);
       __syncthreads();
+      SK_TLC(2);
       if (warp < R) {  // warp w finishes row r0 + w
         const double m0 = half_m[0][warp], m1 = half_m[1][warp];
         const double mm = vmax(m0, m1);
@@ -744,6 +750,7 @@ __device__ void sinkhorn_run_seeded(const SkParams& p, unsigned char* smem_raw) 
         u_chunk[warp] = 0.0; uh_chunk[warp] = 0.f;
       }
       __syncthreads();
+      SK_TLC(3);
 #pragma unroll
       for (int k = 0; k < KG; ++k) {
         const int g = tid + kSkThreads * k;
@@ -785,6 +792,7 @@ __device__ void sinkhorn_run_seeded(const SkParams& p, unsigned char* smem_raw) 
           }
         }
       }
+      SK_TLC(4);
       // (no third barrier: u_chunk / half_* are rewritten only behind the next chunk's first barrier)
     }
 #pragma unroll
