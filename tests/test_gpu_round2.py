@@ -510,3 +510,18 @@ def test_screened_mixed_sinkhorn_wide_row_offsets_and_nan():
     Mn[3, 7] = float("nan")
     _, lu, lv, st, err = _sk(Mn, 0.5, "fp64-mixed", 5)
     assert np.isnan(lu[3]) and np.isnan(lv[7])
+
+
+@pytest.mark.parametrize("n0,n1", [(64, 9000), (40, 12288)])
+def test_screened_mixed_sinkhorn_wide_matrices(n0, n1):
+    """n1 > 8192 leaves the seeded solver (one column panel) for the generic sweep, whose mixed mode screens with
+    thresholds from row / block maxima: same potentials as the unscreened and the all-float64 solvers."""
+    g = torch.Generator().manual_seed(n1)
+    M = torch.rand(n0, n1, generator=g) * 40.0 + 5.0
+    for iters in (1, 12):
+        _, lu, lv, st, _ = _sk(M, 0.05, "fp64-mixed", iters)
+        _, lu0, lv0, st0, _ = _sk(M, 0.05, "fp64-mixed-unscreened", iters)
+        _, lu1, lv1, st1, _ = _sk(M, 0.05, "fp64", iters)
+        assert st[2] == 2 and st[3] == 0 and st0[2] == 2 and st1[2] == 1
+        assert np.abs(lu - lu0).max() < 1e-6 and np.abs(lv - lv0).max() < 1e-6, iters
+        assert np.abs(lu - lu1).max() < 2e-6 and np.abs(lv - lv1).max() < 2e-6, iters
