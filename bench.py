@@ -432,6 +432,8 @@ def main():
                                 f"({world} shard(s) in this run; BASELINE: 4)",
                       "ms_per_shard_coupling": max_over_ranks(c4_ms), "shard_couplings_per_s": world * 1e3 / max_over_ranks(c4_ms),
                       "arithmetic": {0: "fp32", 1: "fp64", 2: "fp64-mixed"}.get(st4[2], st4[2]),
+                      "solver": {0: "generic sweep", 1: "seeded fp32 screening (thresholds from the previous iteration's "
+                                 "log-sum-exps; only the plan's support takes the float64 path)"}.get(st4[3], st4[3]),
                       "row_marginal_max_rel_err": float((P4.sum(1) * 4096 - 1).abs().max().item()),
                       "draw_flags": st4[0] & 3,
                       "note": "row marginals are exact by construction after the final row update; the column marginals of "
