@@ -301,3 +301,68 @@ def test_sharded_trajectory_gloo_world2(n):
         assert full == want
         lo, hi = cdist.shard_bounds(n, 2, rank)
         assert lshape == [3, hi - lo, 2]
+
+
+# ------------------------------------------------------------------ facts the kernels rely on (CPU, no library calls)
+def _eval_c_fraction_table(text):
+    """A brace initialiser of rk_tableau.h ('{1.f / 5, 0, ...}', '(float)(35.0 / 384 - ...)') -> nested lists of
+    floats rounded to fp32 the way the C compiler rounds them."""
+    import re
+    t = text.replace("\\\n", " ")
+    t = re.sub(r"\(float\)", "", t)
+    t = re.sub(r"(\d+(?:\.\d*)?)f\b", r"\1", t)
+    t = t.replace("{", "[").replace("}", "]")
+    return eval(t, {"__builtins__": {}})
+
+
+def test_rk_tableau_header_is_the_oracles_dormand_prince_tableau():
+    """csrc/rk_tableau.h feeds both rk.cu's device constants and the stage row cfm_mlp_forward_rkstage_f32 hands to the
+    fused MLP kernel: every coefficient equals the oracle's (SciPy-pinned) Dormand-Prince tableau rounded to fp32."""
+    import re
+    from oracle import vector_field as vf
+    src = open(os.path.join(ROOT, "cfm_b200", "csrc", "rk_tableau.h")).read()
+
+    def macro(name):
+        m = re.search(r"#define\s+" + name + r"\s+(.*?)(?=\n#define|\n/\*|\Z)", src, re.S)
+        assert m, name
+        return _eval_c_fraction_table(m.group(1).strip())
+
+    c, a, e = macro("CFM_RK_C_INIT"), macro("CFM_RK_A_INIT"), macro("CFM_RK_E_INIT")
+    f32 = lambda v: float(np.float32(v))  # noqa: E731
+    assert [f32(v) for v in c] == [f32(v) for v in vf._C]
+    for s in range(7):
+        row = list(vf._A[s]) + [0.0] * (6 - len(vf._A[s]))
+        # the header writes e.g. 44.f / 45: an fp32 quotient of exactly representable integers == fp32(44 / 45)
+        assert [f32(v) for v in a[s]] == [f32(v) for v in row], s
+    assert [f32(v) for v in e] == [f32(v) for v in vf._BERR]
+
+
+def test_seeded_screening_bound_holds_on_sinkhorn_iterates():
+    """The float64-potential Sinkhorn solver skips terms below  previous LSE + min(change of the other potential) - 34:
+    that is safe because the new log-sum-exp of every row (column) is bounded below by the previous one plus that
+    minimum.  Checked on real iterates of the oracle's log-domain solver, together with the size of the support the
+    threshold leaves (the reason the screening pays)."""
+    from scipy.special import logsumexp
+    rng = np.random.default_rng(0)
+    n, d = 300, 64
+    x0, x1 = rng.standard_normal((n, d)), rng.standard_normal((n, d))
+    M = ((x0[:, None, :] - x1[None, :, :]) ** 2).sum(-1).astype(np.float32)
+    Mr = (-M / np.float32(0.1)).astype(np.float32).astype(np.float64)
+    u, v = np.zeros(n), -np.log(n) - logsumexp(Mr, axis=0)
+    lse_r_prev = None
+    for it in range(12):
+        lse_r = logsumexp(Mr + v[None, :], axis=1)
+        if lse_r_prev is not None:
+            assert (lse_r >= lse_r_prev + dv.min() - 1e-9).all()            # rows: bound with the v change
+            thr = lse_r_prev + dv.min() - 34.0
+            kept = (Mr + v[None, :] > thr[:, None])
+            dropped = np.where(kept, -np.inf, Mr + v[None, :])
+            assert (logsumexp(dropped, axis=1) - lse_r).max() < -25.0         # what is skipped is < e^-25 of the result
+            assert kept.sum() < 0.05 * n * n                                  # ... and almost everything is skipped
+        u_new = -np.log(n) - lse_r
+        du = u_new - u
+        lse_c_prev = -np.log(n) - v                                           # LSE_j(Mr + u_old) that produced v
+        lse_c = logsumexp(Mr + u_new[:, None], axis=0)
+        assert (lse_c >= lse_c_prev + du.min() - 1e-9).all()                  # columns: bound with the u change
+        v_new = -np.log(n) - lse_c
+        dv, u, v, lse_r_prev = v_new - v, u_new, v_new, lse_r
