@@ -97,7 +97,9 @@ class OTPlanSampler:
 
     num_iter_max, stop_thr : POT's ``numItermax`` / ``stopThr`` for Sinkhorn (defaults 1000, 1e-9).
     precision : 'auto' | 'fp32' | 'fp64' | 'fp64-mixed' exponent arithmetic of the Sinkhorn kernel
-        ('fp64-mixed': float64 potentials and exponent arguments, fp32 exponentials).
+        ('fp64-mixed': float64 potentials and exponent arguments, fp32 exponentials, negligible terms screened out in
+        fp32 -- what 'auto' resolves to when |M/reg| > 64; 'fp64-mixed-unscreened' evaluates every term and
+        'fp32-generic' forces the fp32 arithmetic onto the generic kernel: cross-checks).
     stall_tol : stop once an fp32 fixed point is reached (see include/cfm_b200.h); 0 disables.
     cost_algo : 0 auto (fp16x3 tensor-core path for aligned shapes; SIMT for exact OT), 1 SIMT fp32,
         2 tcgen05 3xTF32 (round-1 path, kept for A/B), 3 tcgen05 fp16x3.
