@@ -8,9 +8,9 @@
 //     acc0 += A_hi . B_hi                     (TMEM accumulator 0)
 //     acc1 += A_hi . B_lo + A_lo . B_hi       (TMEM accumulator 1, carries the common factor 2^11)
 //     D     = acc0 + acc1 * 2^-11             (epilogue)
-// drops only the lo.lo term (2^-22 relative): measured on the CPU emulation 2.7e-8 of sum|a||b| at
-// d = 784 (3xTF32 with truncating splits: 1.1e-7), MLP 785-256-256-256-784 1.8e-7 in max norm
-// (3xTF32 8.3e-7; fp32 FMA 8.3e-7).  Range: fp16 tops out at 65504, so producers scale rows by a power of
+// drops only the lo.lo term (2^-22 relative): the NumPy emulation of the representation
+// (tests/test_host.py::test_fp16x3_operand_split_emulation) gives 1.5e-8 of sum|a||b| at d = 784,
+// 3xTF32 with truncating splits 7e-8.  Range: fp16 tops out at 65504, so producers scale rows by a power of
 // two where the data is unbounded (cost matrix: per-row scales, exact) and saturate otherwise.
 //
 // Same persistent warp-specialised structure as gemm_tc.cuh (warp 0 TMA producer, warp 1 single-thread MMA

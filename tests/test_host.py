@@ -366,3 +366,44 @@ def test_seeded_screening_bound_holds_on_sinkhorn_iterates():
         assert (lse_c >= lse_c_prev + du.min() - 1e-9).all()                  # columns: bound with the u change
         v_new = -np.log(n) - lse_c
         dv, u, v, lse_r_prev = v_new - v, u_new, v_new, lse_r
+
+
+def test_fp16x3_operand_split_emulation():
+    """The fp16x3 scheme of csrc/gemm_h3.cuh in NumPy: hi = fp16(x), lo = fp16((x - hi) 2^11), and
+    acc0 = sum hi.hi, acc1 = sum (hi.lo + lo.hi), result acc0 + acc1 2^-11 (products of fp16 numbers are exact in the
+    fp32 the tensor core accumulates in; only lo.lo, 2^-22 relative, is dropped).  Pins the accuracy DESIGN.md 3.0
+    quotes for the representation itself -- 2.7e-8 of sum|a||b| at d = 784 -- against the 3xTF32 split of round 1, and
+    the power-of-two row scaling that keeps unbounded inputs inside fp16's range exactly."""
+    rng = np.random.default_rng(3)
+    n, d = 64, 784
+    a = rng.standard_normal((n, d)).astype(np.float32)
+    b = (rng.standard_normal((n, d)) + 0.3).astype(np.float32)
+
+    def split_h3(x):
+        hi = x.astype(np.float16)
+        lo = ((x - hi.astype(np.float32)) * np.float32(2048.0)).astype(np.float16)
+        return hi.astype(np.float64), lo.astype(np.float64)
+
+    def tf32_trunc(x):
+        return (x.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+    exact = a.astype(np.float64) @ b.astype(np.float64).T
+    scale = np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64).T
+    ah, al = split_h3(a)
+    bh, bl = split_h3(b)
+    h3 = ah @ bh.T + (ah @ bl.T + al @ bh.T) / 2048.0
+    err_h3 = (np.abs(h3 - exact) / scale).max()
+    a_hi = tf32_trunc(a); a_lo = tf32_trunc(a - a_hi)
+    b_hi = tf32_trunc(b); b_lo = tf32_trunc(b - b_hi)
+    t3 = (a_hi.astype(np.float64) @ b_hi.astype(np.float64).T + a_hi.astype(np.float64) @ b_lo.astype(np.float64).T
+          + a_lo.astype(np.float64) @ b_hi.astype(np.float64).T)
+    err_t3 = (np.abs(t3 - exact) / scale).max()
+    assert err_h3 < 6e-8 and err_h3 < err_t3, (err_h3, err_t3)
+    # rows scaled by exact powers of two (what the cost path does for unbounded data): same result, no overflow
+    big = a * np.float32(3.0e5)
+    s = np.exp2(np.floor(np.log2(32768.0 / np.abs(big).max(1)))).astype(np.float32)  # row max -> [16384, 32768)
+    assert np.isfinite((big * s[:, None]).astype(np.float16)).all()
+    gh, gl = split_h3(big * s[:, None])
+    h3s = (gh @ bh.T + (gh @ bl.T + gl @ bh.T) / 2048.0) / s[:, None].astype(np.float64)
+    exact_big = big.astype(np.float64) @ b.astype(np.float64).T
+    assert (np.abs(h3s - exact_big) / (np.abs(big).astype(np.float64) @ np.abs(b).astype(np.float64).T)).max() < 6e-8
