@@ -469,8 +469,8 @@ __device__ void sinkhorn_run(const SkParams& p, unsigned char* smem_raw) {
 
 
 // ---- float64-potential mode, seeded screening (BASELINE config 4 regime) -------------------------------------
-// The potentials of consecutive Sinkhorn iterations differ by a few units only (measured at config 4: |du|, |dv| < 5
-// from the first iteration on), and every log-sum-exp of this iteration is bounded below by the one the previous
+// The potentials of consecutive Sinkhorn iterations do not DROP by more than a few units (config 4: min du, min dv > -5
+// from the first iteration on; scripts/sim/sinkhorn_screening.py), and every log-sum-exp of this iteration is bounded below by the one the previous
 // iteration computed for the same row / column:
 //     LSE_i(Mr_i. + v_new) >= LSE_i(Mr_i. + v_old) + min_j (v_new_j - v_old_j),      (rows; columns alike with u)
 // because every term grows by at least that minimum.  So the threshold below which a term is negligible is known
